@@ -1,0 +1,257 @@
+"""Importance-sampling coder: the reference's entry points (code/coded_importance_sampler.py) on the
+B200 engine.  Names, argument order, defaults, return types and error messages follow the reference so
+`pln.py` can import this module in place of the original:
+
+    code_importance_sample            CIS:29-79
+    decode_importance_sample          CIS:82-109
+    code_grouped_importance_sample    CIS:112-274
+    decode_grouped_importance_sample  CIS:277-363
+
+`target` / `proposal` are duck-typed exactly as in the reference (only .loc, .scale, .dtype are read);
+their arrays may be numpy, torch (CPU or CUDA) or any DLPack producer.  `sess` is accepted and ignored.
+`*_batch` variants run many reference calls in one launch sequence (same results per call).
+"""
+import numpy as np
+import torch
+
+from . import engine as E
+from ._lib import CwqError
+from .binary_io import elias_delta_code, elias_delta_decode
+
+__all__ = ["code_importance_sample", "decode_importance_sample", "code_grouped_importance_sample",
+           "decode_grouped_importance_sample", "code_grouped_importance_sample_batch",
+           "decode_grouped_importance_sample_batch"]
+
+
+class _Dist:
+    def __init__(self, loc, scale):
+        self.loc, self.scale = loc, scale
+        self.dtype = np.float32
+
+
+def _check_dtype(dist, what):
+    if not E.is_float32(getattr(dist, "dtype", None)):
+        raise Exception("{} datatype must be float32!".format(what))
+
+
+def _u16_view(t):
+    return t.cpu().numpy().view(np.uint16)
+
+
+# ----------------------------------------------------------------------------------------------
+# per-group entry points
+# ----------------------------------------------------------------------------------------------
+def code_importance_sample(t_loc, t_scale, p_loc, p_scale, n_coding_bits, seed, return_index_only=False):
+    """One group (CIS:29-79): K = ceil(exp(KL(t||p))) candidates from p, index of the largest
+    importance weight.  Returns (best_sample f32[1, G], Elias-delta bitcode bytes) or, with
+    return_index_only, (best_sample, index + 1).  n_coding_bits is unused, as in the reference."""
+    dev = E.cuda_device()
+    tl, ts, pl, ps = (E.as_device_f32(x, dev) for x in (t_loc, t_scale, p_loc, p_scale))
+    G = tl.numel()
+    if G == 0:
+        best, index = np.zeros((1, 0), np.float32), 0
+    else:
+        spec = E.SegmentSpec(G, seed, 1.0, 0, float("inf"), True)
+        job = E.ISJob(tl, ts, pl, ps, [spec], forced_starts=[np.array([0, G])]).prepare().encode().decode()
+        index = int(job.host_indices(0)[0])
+        best = job.sample.cpu().numpy().reshape(1, G)
+    if return_index_only:
+        return best, np.int64(index + 1)
+    return best, elias_delta_code(index + 1).encode("utf-8")
+
+
+def decode_importance_sample(sample_index, p_loc, p_scale, seed, use_index=False):
+    """One group (CIS:82-109).  With use_index the 1-based index is given directly and only the sample
+    f32[1, G] is returned; otherwise sample_index is the remaining bitstream and the result is
+    (sample, code_length, index, samples[index + 1, G]) as in the reference."""
+    dev = E.cuda_device()
+    pl, ps = E.as_device_f32(p_loc, dev), E.as_device_f32(p_scale, dev)
+    G = pl.numel()
+    if use_index:
+        index = int(sample_index) - 1
+        code_length = None
+    else:
+        num, code_length = elias_delta_decode(sample_index)
+        index = num - 1
+    s32 = int(seed) & 0xFFFFFFFF
+    if use_index:
+        z = E.draw_candidates(s32, index, 1, G, dev)
+        return (ps[None] * z + pl[None]).cpu().numpy()
+    z = E.draw_candidates(s32, 0, index + 1, G, dev)   # the reference materialises rows 0..index (CIS:104-109)
+    samples = (ps[None] * z + pl[None]).cpu().numpy()
+    return samples[-1:], np.int64(code_length), np.int64(index), samples
+
+
+# ----------------------------------------------------------------------------------------------
+# grouped entry points
+# ----------------------------------------------------------------------------------------------
+def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, stage,
+                  shard=None):
+    """Shared driver.  stage: 'groups' | 'indices' | 'full'.  Returns (job, per-segment sizes)."""
+    dev = E.cuda_device()
+    ns = len(targets)
+
+    def per(v):
+        return list(v) if isinstance(v, (list, tuple)) else [v] * ns
+
+    seeds, nb, mg, dl = per(seeds), per(n_bits_per_group), per(max_group_size_bits), per(dim_kl_bit_limit)
+    for t, p in zip(targets, proposals):
+        _check_dtype(t, "Target")
+        _check_dtype(p, "Proposal")
+    q_loc = [E.as_device_f32(t.loc, dev, "Target") for t in targets]
+    q_scale = [E.as_device_f32(t.scale, dev, "Target") for t in targets]
+    p_loc = [E.as_device_f32(p.loc, dev, "Proposal") for p in proposals]
+    p_scale = [E.as_device_f32(p.scale, dev, "Proposal") for p in proposals]
+    sizes = [int(x.numel()) for x in p_loc]
+    specs = [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
+    cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
+    job = E.ISJob(cat(q_loc), cat(q_scale), cat(p_loc), cat(p_scale), specs).prepare()
+    if stage == "groups":
+        return job
+    if shard is None:
+        job.encode()
+    else:
+        shard(job)
+    if stage == "indices":
+        return job
+    job.decode().pack()
+    return job
+
+
+def _segment_result(job, s, host, return_indices):
+    g0, g1 = job.segment_group_range(s)
+    a, b = job.table.starts[s], job.table.starts[s] + job.table.specs[s].n
+    sample = host["sample"][a:b].copy()
+    starts = host["starts"][g0:g1 + 1] - a
+    o0, o1 = int(host["seg_outlier_off"][s]), int(host["seg_outlier_off"][s + 1])
+    outlier_extras = (host["outlier_idx"][o0:o1].copy(), host["outlier_q"][o0:o1].copy())
+    if return_indices:
+        indices = [np.int64(i) + 1 for i in host["index"][g0:g1]]
+        return sample, indices, starts, outlier_extras
+    bit0, bit1 = int(host["bit_off"][g0]), int(host["bit_off"][g1])
+    bitcode = E.bits_to_ascii(host["bits"], bit1 - bit0, bit0)
+    return sample, bitcode, starts, outlier_extras
+
+
+def _host_views(job, with_bits):
+    n_out = int(job.seg_outlier_off[-1].item())
+    host = {
+        "sample": job.sample.cpu().numpy(),
+        "starts": job.groups.starts.cpu().numpy(),
+        "index": job.index.cpu().numpy().view(np.uint32),
+        "seg_outlier_off": job.seg_outlier_off.cpu().numpy(),
+        "outlier_idx": job.outlier_idx[:n_out].cpu().numpy(),
+        "outlier_q": _u16_view(job.outlier_q[:n_out]),
+    }
+    if with_bits:
+        host["bit_off"] = job.bit_off.cpu().numpy()
+        total_bytes = (int(host["bit_off"][-1]) + 7) // 8
+        host["bits"] = job.bits[:total_bytes].cpu().numpy()
+    return host
+
+
+def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits=4,
+                                         dim_kl_bit_limit=12, return_indices=False, shard=None):
+    """Many reference calls in one launch sequence.  seed / n_bits_per_group / max_group_size_bits /
+    dim_kl_bit_limit may be scalars or per-call lists.  Returns a list with, per call, exactly what
+    code_grouped_importance_sample returns.  `shard` (see distributed.py) replaces the single-GPU
+    encode stage by a sharded one."""
+    job = _encode_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, "full",
+                        shard=shard)
+    host = _host_views(job, with_bits=not return_indices)
+    return [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+
+
+def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_group, max_group_size_bits=4,
+                                   dim_kl_bit_limit=12, return_group_indices_only=False, return_indices=False,
+                                   return_indices_only=False):
+    """CIS:112-274.  Returns (sample f32[N], bitcode bytes of '0'/'1', group_start_indices int64
+    ndarray ending in N, (outlier_indices int64[M], outlier_samples uint16[M]))."""
+    _check_dtype(target, "Target")
+    _check_dtype(proposal, "Proposal")
+    num_dimensions = int(np.prod(np.shape(proposal.loc))) if not hasattr(proposal.loc, "numel") else int(proposal.loc.numel())
+    if num_dimensions == 0:
+        # CIS:183-204 with an empty range: starts [0, 0], one empty group, K = 1, index 0
+        starts = np.array([0, 0], dtype=np.int64)
+        empty = (np.zeros(0, np.int64), np.zeros(0, np.uint16))
+        if return_group_indices_only:
+            return starts, []
+        if return_indices_only:
+            return (np.int64(1),)
+        if return_indices:
+            return np.zeros(0, np.float32), [np.int64(1)], starts, empty
+        return np.zeros(0, np.float32), b"1", starts, empty
+    stage = "groups" if return_group_indices_only else ("indices" if return_indices_only else "full")
+    job = _encode_batch([target], [proposal], seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, stage)
+    if return_group_indices_only:
+        # CIS:192: the KL (bits) of every group closed inside the loop, i.e. all but the last
+        kls = job.total_kl.cpu().numpy()
+        return job.host_starts(0), [k / np.log(2) for k in kls[:-1]]
+    if return_indices_only:
+        return tuple(np.int64(i) + 1 for i in job.host_indices(0))
+    host = _host_views(job, with_bits=not return_indices)
+    return _segment_result(job, 0, host, return_indices)
+
+
+def decode_grouped_importance_sample_batch(bitcodes, group_start_indices, proposals, seed, outlier_indices,
+                                           outlier_samples, use_indices=False):
+    """Batch of decode calls; group_start_indices[s] must already end with the number of dimensions."""
+    dev = E.cuda_device()
+    ns = len(proposals)
+    seeds = list(seed) if isinstance(seed, (list, tuple)) else [seed] * ns
+    for p in proposals:
+        _check_dtype(p, "Proposal")
+    p_loc = [E.as_device_f32(p.loc, dev, "Proposal") for p in proposals]
+    p_scale = [E.as_device_f32(p.scale, dev, "Proposal") for p in proposals]
+    sizes = [int(x.numel()) for x in p_loc]
+    specs = [E.SegmentSpec(sizes[i], seeds[i], 1.0, 0, float("inf"), True) for i in range(ns)]
+    table = E.SegmentTable(specs, dev)
+    groups = E._forced_groups(group_start_indices, table, dev)
+    idx_parts = []
+    for s in range(ns):
+        ng = len(group_start_indices[s]) - 1
+        if use_indices:
+            part = np.asarray([int(v) - 1 for v in bitcodes[s]], dtype=np.int64)
+            if part.size != ng:
+                raise CwqError("need one index per group")
+            idx_parts.append(part.astype(np.uint32))
+        else:
+            part, _ = E.elias_delta_parse(bitcodes[s], ng)
+            idx_parts.append(part)
+    index = torch.from_numpy(np.concatenate(idx_parts).view(np.int32)).to(dev)
+    cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
+    pl, ps = cat(p_loc), cat(p_scale)
+    sample = torch.empty(table.n, dtype=torch.float32, device=dev)
+    E._lib.call("cwq_is_decode", E._ptr(groups.starts), E._ptr(groups.group_seed), E._ptr(groups.gid), E._ptr(index), table.n,
+                E._ptr(pl), E._ptr(ps), E._ptr(sample), E._stream())
+    pos, q = [], []
+    for s in range(ns):
+        oi = np.asarray(outlier_indices[s], dtype=np.int64).reshape(-1)
+        oq = np.asarray(outlier_samples[s]).reshape(-1).astype(np.uint16)
+        if oi.size != oq.size:
+            raise CwqError("outlier_indices and outlier_samples differ in length")
+        if oi.size and (oi.min() < 0 or oi.max() >= sizes[s]):
+            raise CwqError("outlier index out of range")
+        pos.append(oi + table.starts[s])
+        q.append(oq)
+    pos, q = np.concatenate(pos), np.concatenate(q)
+    if pos.size:
+        pos_d = torch.from_numpy(pos).to(dev)
+        q_d = torch.from_numpy(q.view(np.int16)).to(dev)
+        E._lib.call("cwq_outlier_decode", E._ptr(sample), E._ptr(pos_d), E._ptr(q_d), int(pos.size), E._stream())
+    host = sample.cpu().numpy()
+    return [host[table.starts[s]:table.starts[s] + sizes[s]].copy() for s in range(ns)]
+
+
+def decode_grouped_importance_sample(sess, bitcode, group_start_indices, proposal, n_bits_per_group, seed,
+                                     outlier_indices, outlier_samples, use_indices=False):
+    """CIS:277-363 -> f32[N].  As in the reference, N is appended to the caller's group_start_indices
+    list (CIS:294) and n_bits_per_group is unused.  use_indices follows the evident intent of
+    CIS:88-96 (bitcode is then a sequence of 1-based indices); the shipped branch cannot run."""
+    _check_dtype(proposal, "Proposal")
+    num_dimensions = int(np.prod(np.shape(proposal.loc))) if not hasattr(proposal.loc, "numel") else int(proposal.loc.numel())
+    group_start_indices.append(num_dimensions)
+    if num_dimensions == 0:
+        return np.zeros(0, np.float32)
+    return decode_grouped_importance_sample_batch([bitcode], [group_start_indices], [proposal], seed, [outlier_indices],
+                                                  [outlier_samples], use_indices)[0]

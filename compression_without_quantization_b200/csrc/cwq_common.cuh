@@ -1,0 +1,162 @@
+// cwq_common.cuh -- error plumbing, segment lookup and a small device-wide scan used by the O(N)
+// stages (grouping compaction, unit offsets, bit offsets, outlier compaction).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/cwq.h"
+
+namespace cwq {
+
+void set_error(const std::string& msg);
+
+#define CWQ_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      ::cwq::set_error(std::string(__func__) + ": " + (msg));    \
+      return CWQ_ERR_ARG;                                        \
+    }                                                            \
+  } while (0)
+
+#define CWQ_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      ::cwq::set_error(std::string(__func__) + ": " + #expr + ": " + cudaGetErrorString(e_));  \
+      return CWQ_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+// every kernel launch of the library goes through this: it also feeds cwq_launch_count()
+void count_launches(int n);
+#define CWQ_LAUNCH_CHECK()            \
+  do {                                \
+    ::cwq::count_launches(1);         \
+    CWQ_CUDA(cudaGetLastError());     \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Workspace {
+  char* base;
+  size_t size, used;
+  Workspace(void* p, size_t n) : base((char*)p), size(n), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (used + bytes > size) return nullptr;
+    T* r = (T*)(base + used);
+    used += bytes;
+    return r;
+  }
+};
+
+__device__ __forceinline__ int find_segment(const cwq_segment* __restrict__ segs, int n_seg, long long i) {
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].start <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan of in(i), i in [0, n), delivered to out(i, exclusive_prefix, value).
+// Three launches: per-tile sums, one-block scan of the sums, per-tile scan + delivery.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* smem /*[33]*/, T& block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < nwarps ? smem[lane] : T(0);
+    T wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < nwarps) smem[lane] = wi - w;
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  T r = smem[warp] + incl - v;
+  block_total = smem[32];
+  __syncthreads();
+  return r;
+}
+
+template <typename T, class InF>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(InF in, long long n, T* __restrict__ tile_sums) {
+  __shared__ T sm[33];
+  long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  T s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j)
+    if (base + j < n) s += in(base + j);
+  T total;
+  block_exclusive_scan<T>(s, sm, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_of_sums(T* __restrict__ tile_sums, long long nt, T* __restrict__ total_out) {
+  __shared__ T sm[33];
+  long long per = (nt + blockDim.x - 1) / blockDim.x;
+  long long b = (long long)threadIdx.x * per, e = b + per < nt ? b + per : nt;
+  T s = 0;
+  for (long long i = b; i < e; ++i) s += tile_sums[i];
+  T total;
+  T off = block_exclusive_scan<T>(s, sm, total);
+  for (long long i = b; i < e; ++i) { T v = tile_sums[i]; tile_sums[i] = off; off += v; }
+  if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+
+template <typename T, class InF, class OutF>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_deliver(InF in, OutF out, long long n, const T* __restrict__ tile_offsets) {
+  __shared__ T sm[33];
+  long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  T v[SCAN_ITEMS];
+  T s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = (base + j < n) ? in(base + j) : T(0); s += v[j]; }
+  T total;
+  T pre = block_exclusive_scan<T>(s, sm, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (base + j < n) out(base + j, pre, v[j]);
+    pre += v[j];
+  }
+}
+
+inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+// tile_sums must hold scan_tiles(n) entries; total_out (device) may be null
+template <typename T, class InF, class OutF>
+cudaError_t device_exclusive_scan(InF in, OutF out, long long n, T* tile_sums, T* total_out, cudaStream_t st) {
+  if (n <= 0) {
+    if (total_out) return cudaMemsetAsync(total_out, 0, sizeof(T), st);
+    return cudaSuccess;
+  }
+  long long nt = scan_tiles(n);
+  k_scan_tile_sums<T, InF><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tile_sums);
+  k_scan_of_sums<T><<<1, 1024, 0, st>>>(tile_sums, nt, total_out);
+  k_scan_deliver<T, InF, OutF><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
+  count_launches(3);
+  return cudaGetLastError();
+}
+
+}  // namespace cwq

@@ -1,0 +1,715 @@
+// cwq_samplers.cu -- the candidate loops: importance-sampler scoring/argmax, greedy persistent
+// step loop, the decode (regenerate-from-index) kernels, outliers, index->bit packing and the
+// debug view of the candidate stream.  Reference lines are cited at each extern "C" entry in cwq.h.
+//
+// Work decomposition of the importance sampler (the dominant kernel, k_is_score):
+//   a group's K candidates are cut into UNITs of 1024; a WARP claims a short run of consecutive
+//   units from a global counter, scores 32 candidates at a time (one candidate per lane, its
+//   ceil(G/4) Philox blocks and Box-Muller pairs generated in registers, never stored), keeps a
+//   per-lane (score, index) best, shuffle-reduces it and publishes one 64-bit atomicMax per run.
+//   No __syncthreads, no HBM traffic beyond the 8 B/dim coefficients and 8 B/group keys.
+#include "cwq_common.cuh"
+#include "cwq_spec.cuh"
+#include <atomic>
+
+namespace cwq {
+
+using ull = unsigned long long;
+
+// ------------------------------------------------------------------------------------------
+// importance sampler: encode
+// ------------------------------------------------------------------------------------------
+constexpr int IS_THREADS = 256;
+constexpr int IS_WARPS = IS_THREADS / 32;
+constexpr int UNIT_CAND = 1024;  // candidates per unit
+constexpr int UNIT_BATCH = 4;    // units claimed per atomic
+
+struct UnitCount {
+  const int* K;
+  long long g0;
+  __device__ ull operator()(long long j) const { return (ull)((K[g0 + j] + UNIT_CAND - 1) / UNIT_CAND); }
+};
+struct UnitDeliver {
+  ull* unit_off;
+  ull* keys;
+  long long g0;
+  __device__ void operator()(long long j, ull pre, ull) const {
+    unit_off[j] = pre;
+    keys[g0 + j] = KEY_INIT;
+  }
+};
+__global__ void k_units_finish(ull* unit_off, long long ng, const ull* total, ull* counter) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { unit_off[ng] = *total; *counter = 0; }
+}
+
+__device__ __forceinline__ ull warp_max_key(ull key) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ull other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  return key;
+}
+
+// candidates [kb, ke) of one group, NQ quads of coefficients staged in this warp's shared slice
+template <int NQ>
+__device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
+                                               int lane, float& best, uint32_t& bestk) {
+  for (uint32_t k = kb + lane; k < ke; k += 32) {
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float z[4];
+      normal_quad(sseed, k, (uint32_t)q, z);
+      float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
+      acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
+      acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
+      acc0 = __fmaf_rn(z[2], __fmaf_rn(c23.x, z[2], c23.y), acc0);
+      acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
+    }
+    float s = __fadd_rn(acc0, acc1);
+    if (s > best) { best = s; bestk = k; }
+  }
+}
+
+// any group size: coefficients read through the read-only path (warp-uniform addresses)
+__device__ __forceinline__ void is_score_range_generic(const float2* __restrict__ coef, int G, uint32_t sseed, uint32_t kb,
+                                                       uint32_t ke, int lane, float& best, uint32_t& bestk) {
+  const int nq = (G + 3) >> 2;
+  for (uint32_t k = kb + lane; k < ke; k += 32) {
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int q = 0; q < nq; ++q) {
+      float z[4];
+      normal_quad(sseed, k, (uint32_t)q, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int d = 4 * q + j;
+        float2 c = d < G ? __ldg(&coef[d]) : make_float2(0.0f, 0.0f);
+        float w = __fmaf_rn(c.x, z[j], c.y);
+        if (j & 1) acc1 = __fmaf_rn(z[j], w, acc1); else acc0 = __fmaf_rn(z[j], w, acc0);
+      }
+    }
+    float s = __fadd_rn(acc0, acc1);
+    if (s > best) { best = s; bestk = k; }
+  }
+}
+
+__global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
+                                                         const int* __restrict__ K, const uint32_t* __restrict__ gseed,
+                                                         long long g0, long long ng, const ull* __restrict__ unit_off,
+                                                         ull* __restrict__ counter, ull* __restrict__ keys) {
+  __shared__ float4 s_coef[IS_WARPS][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ull n_units = unit_off[ng];
+  float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
+  for (;;) {
+    ull u = 0;
+    if (lane == 0) u = atomicAdd(counter, (ull)UNIT_BATCH);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_units) break;
+    const ull u_end = u + UNIT_BATCH < n_units ? u + UNIT_BATCH : n_units;
+    long long lo = 0, hi = ng - 1;
+    while (lo < hi) {
+      long long mid = (lo + hi + 1) >> 1;
+      if (unit_off[mid] <= u) lo = mid; else hi = mid - 1;
+    }
+    long long j = lo;
+    while (u < u_end) {
+      const ull off_j = unit_off[j], off_n = unit_off[j + 1];
+      const ull ue = u_end < off_n ? u_end : off_n;
+      const long long g = g0 + j;
+      const uint32_t Kg = (uint32_t)K[g];
+      const uint32_t kb = (uint32_t)(u - off_j) * UNIT_CAND;
+      const ull ke64 = (ue - off_j) * (ull)UNIT_CAND;
+      const uint32_t ke = ke64 < Kg ? (uint32_t)ke64 : Kg;
+      const long long s = starts[g];
+      const int G = (int)(starts[g + 1] - s);
+      const uint32_t sseed = gseed[g];
+      float best = __uint_as_float(0xff800000u);
+      uint32_t bestk = 0xffffffffu;
+      if (G <= 16) {
+        __syncwarp();
+        if (lane < 16) my_coef[lane] = lane < G ? coef[s + lane] : make_float2(0.0f, 0.0f);
+        __syncwarp();
+        const float4* sc = s_coef[warp];
+        switch ((G + 3) >> 2) {
+          case 0: is_score_range<0>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 1: is_score_range<1>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 2: is_score_range<2>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 3: is_score_range<3>(sc, sseed, kb, ke, lane, best, bestk); break;
+          default: is_score_range<4>(sc, sseed, kb, ke, lane, best, bestk); break;
+        }
+      } else {
+        is_score_range_generic(coef + s, G, sseed, kb, ke, lane, best, bestk);
+      }
+      ull key = bestk == 0xffffffffu ? 0ull : pack_key(best, bestk);
+      key = warp_max_key(key);
+      if (lane == 0 && key != 0ull) atomicMax(&keys[g], key);
+      u = ue;
+      ++j;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, long long g0, long long g1,
+                                                  uint32_t* __restrict__ index) {
+  long long g = g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < g1) index[g] = key_index(keys[g]);
+}
+
+// ------------------------------------------------------------------------------------------
+// importance sampler: decode (row index[g] of each group's table), un-rescaled
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_is_decode(const long long* __restrict__ starts, const uint32_t* __restrict__ gseed,
+                                                   const int* __restrict__ gid, const uint32_t* __restrict__ index,
+                                                   long long n, const float* __restrict__ p_loc,
+                                                   const float* __restrict__ p_scale, float* __restrict__ sample) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int g = gid[i];
+  uint32_t d = (uint32_t)(i - starts[g]);
+  float z[4];
+  normal_quad(gseed[g], index[g], d >> 2, z);
+  float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
+  sample[i] = __fadd_rn(__fmul_rn(p_scale[i], zz), p_loc[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// outliers
+// ------------------------------------------------------------------------------------------
+struct OutlierCount {
+  const uint8_t* mask;
+  __device__ uint32_t operator()(long long i) const { return (uint32_t)((mask[i] >> 1) & 1); }
+};
+struct OutlierDeliver {
+  const uint8_t* mask;
+  const float* q_loc;
+  const float* q_scale;
+  const cwq_segment* segs;
+  int n_seg;
+  float* sample;
+  long long* outlier_idx;
+  uint16_t* outlier_q;
+  long long* seg_outlier_off;
+  __device__ void operator()(long long i, uint32_t pre, uint32_t cnt) const {
+    if (cnt == 0) return;
+    int s = find_segment(segs, n_seg, i);
+    long long local = i - segs[s].start;
+    float z[4];
+    normal_quad(segs[s].seed + OUTLIER_STREAM_OFFSET, (uint32_t)local, 0u, z);
+    float v = __fadd_rn(__fmul_rn(q_scale[i], z[0]), q_loc[i]);
+    sample[i] = v;
+    outlier_idx[pre] = local;
+    outlier_q[pre] = quantize_u16(v);
+  }
+};
+// seg_outlier_off[s] = number of outliers before segment s: counted per segment by one warp each
+__global__ void __launch_bounds__(256) k_seg_outlier_count(const uint8_t* __restrict__ mask, const cwq_segment* __restrict__ segs,
+                                                           int n_seg, unsigned int* __restrict__ counts) {
+  int s = blockIdx.x;
+  if (s >= n_seg) return;
+  unsigned int c = 0;
+  for (long long i = segs[s].start + threadIdx.x; i < segs[s].end; i += blockDim.x) c += (mask[i] >> 1) & 1;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[s], c);
+}
+__global__ void k_seg_outlier_offsets(const unsigned int* __restrict__ counts, int n_seg, long long* __restrict__ off) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long a = 0;
+    for (int s = 0; s < n_seg; ++s) { off[s] = a; a += counts[s]; }
+    off[n_seg] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_outlier_decode(float* __restrict__ sample, const long long* __restrict__ pos,
+                                                        const uint16_t* __restrict__ q, long long m) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  float v = dequantize_u16(q[j]);
+  if (v != 0.0f) sample[pos[j]] = v;  // CIS:361: tf.where(updates == 0, sample, updates)
+}
+
+// ------------------------------------------------------------------------------------------
+// greedy sampler
+// ------------------------------------------------------------------------------------------
+constexpr int GREEDY_THREADS = 512;
+
+__global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* __restrict__ tparam, const long long* __restrict__ starts,
+                                                                  const uint32_t* __restrict__ gseed, long long g0, int n_steps,
+                                                                  uint32_t n_samples, float shard_scale,
+                                                                  uint32_t* __restrict__ indices, float* __restrict__ best_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ ull s_warp_key[GREEDY_THREADS / 32];
+  __shared__ uint32_t s_choice;
+  const long long g = g0 + blockIdx.x;
+  const long long s = starts[g];
+  const int G = (int)(starts[g + 1] - s);
+  const int nq = (G + 3) >> 2, Gp = nq * 4;
+  float2* ce = reinterpret_cast<float2*>(smem_raw);            // (c_d, e_d)
+  float* best = reinterpret_cast<float*>(smem_raw + (size_t)Gp * sizeof(float2));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t group_seed = gseed[g];
+  for (int d = tid; d < Gp; d += GREEDY_THREADS) {
+    best[d] = 0.0f;
+    ce[d] = make_float2(d < G ? __fmul_rn(shard_scale, tparam[s + d].y) : 0.0f, 0.0f);
+  }
+  __syncthreads();
+  for (int step = 0; step < n_steps; ++step) {
+    const uint32_t sseed = 1000u * group_seed + (uint32_t)step;  // CGS:55
+    for (int d = tid; d < G; d += GREEDY_THREADS) {
+      float2 t = tparam[s + d];
+      ce[d].y = __fmul_rn(__fsub_rn(best[d], t.x), t.y);
+    }
+    __syncthreads();
+    float bs = __uint_as_float(0x7f800000u);
+    uint32_t bk = 0xffffffffu;
+    const float4* ce4 = reinterpret_cast<const float4*>(ce);
+    for (uint32_t k = tid; k < n_samples; k += GREEDY_THREADS) {
+      float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q) {
+        float z[4];
+        normal_quad(sseed, k, (uint32_t)q, z);
+        float4 c01 = ce4[2 * q], c23 = ce4[2 * q + 1];
+        float u0 = __fmaf_rn(z[0], c01.x, c01.y);
+        float u1 = __fmaf_rn(z[1], c01.z, c01.w);
+        float u2 = __fmaf_rn(z[2], c23.x, c23.y);
+        float u3 = __fmaf_rn(z[3], c23.z, c23.w);
+        acc0 = __fmaf_rn(u0, u0, acc0);
+        acc1 = __fmaf_rn(u1, u1, acc1);
+        acc0 = __fmaf_rn(u2, u2, acc0);
+        acc1 = __fmaf_rn(u3, u3, acc1);
+      }
+      float sc = __fadd_rn(acc0, acc1);
+      if (sc < bs) { bs = sc; bk = k; }
+    }
+    // argmin, lowest index on ties == argmax of the negated score
+    ull key = bk == 0xffffffffu ? 0ull : pack_key(-bs, bk);
+    key = warp_max_key(key);
+    if (lane == 0) s_warp_key[warp] = key;
+    __syncthreads();
+    if (warp == 0) {
+      ull k2 = lane < GREEDY_THREADS / 32 ? s_warp_key[lane] : 0ull;
+      k2 = warp_max_key(k2);
+      if (lane == 0) {
+        uint32_t choice = k2 == 0ull ? 0u : key_index(k2);
+        s_choice = choice;
+        indices[g * n_steps + step] = choice;
+      }
+    }
+    __syncthreads();
+    const uint32_t choice = s_choice;
+    for (int q = tid; q < nq; q += GREEDY_THREADS) {
+      float z[4];
+      normal_quad(sseed, choice, (uint32_t)q, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) best[4 * q + j] = __fmaf_rn(shard_scale, z[j], best[4 * q + j]);
+    }
+    __syncthreads();
+  }
+  for (int d = tid; d < G; d += GREEDY_THREADS) best_out[s + d] = best[d];
+}
+
+__global__ void __launch_bounds__(256) k_greedy_decode(const long long* __restrict__ starts, const uint32_t* __restrict__ gseed,
+                                                       const int* __restrict__ gid, const uint32_t* __restrict__ indices,
+                                                       long long n, int n_steps, float shard_scale,
+                                                       const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                                                       float* __restrict__ sample) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int g = gid[i];
+  uint32_t d = (uint32_t)(i - starts[g]);
+  uint32_t group_seed = gseed[g];
+  float b = 0.0f;
+  for (int step = 0; step < n_steps; ++step) {
+    float z[4];
+    normal_quad(1000u * group_seed + (uint32_t)step, indices[(long long)g * n_steps + step], d >> 2, z);
+    float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
+    b = __fmaf_rn(shard_scale, zz, b);
+  }
+  sample[i] = __fadd_rn(__fmul_rn(p_scale[i], b), p_loc[i]);
+}
+
+__global__ void __launch_bounds__(256) k_unrescale(const float* __restrict__ best, const float* __restrict__ p_loc,
+                                                   const float* __restrict__ p_scale, long long n, float* __restrict__ sample) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sample[i] = __fadd_rn(__fmul_rn(p_scale[i], best[i]), p_loc[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// index -> bits
+// ------------------------------------------------------------------------------------------
+// OR `len` bits (right-aligned in pattern) into a big-endian-bit-ordered word stream at bit `pos`
+__device__ __forceinline__ void put_bits(uint32_t* words, ull pos, ull pattern, int len) {
+  ull w = pos >> 5;
+  int o = (int)(pos & 31);
+  int remaining = len;
+  while (remaining > 0) {
+    int take = 32 - o < remaining ? 32 - o : remaining;
+    uint32_t chunk = (uint32_t)((pattern >> (remaining - take)) & ((1ull << take) - 1ull));
+    atomicOr(&words[w], chunk << (32 - o - take));
+    remaining -= take;
+    ++w;
+    o = 0;
+  }
+}
+
+__device__ __forceinline__ void elias_delta(uint32_t x, ull& pattern, int& len) {
+  int n = 31 - __clz((int)x);          // floor(log2 x), BIO:11
+  int l = 31 - __clz(n + 1);           // floor(log2 (n+1)), BIO:12
+  pattern = ((ull)(n + 1) << n) | (ull)(x & ((n == 0) ? 0u : (0xffffffffu >> (32 - n))));
+  len = 2 * l + n + 1;
+}
+
+struct EliasLen {
+  const uint32_t* index;
+  __device__ ull operator()(long long g) const {
+    ull p; int len;
+    elias_delta(index[g] + 1u, p, len);
+    return (ull)len;
+  }
+};
+struct EliasDeliver {
+  const uint32_t* index;
+  long long* bit_off;
+  uint32_t* words;
+  __device__ void operator()(long long g, ull pre, ull) const {
+    ull p; int len;
+    elias_delta(index[g] + 1u, p, len);
+    bit_off[g] = (long long)pre;
+    put_bits(words, pre, p, len);
+  }
+};
+__global__ void k_bits_finish(long long* bit_off, long long ng, const ull* total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) bit_off[ng] = (long long)*total;
+}
+__global__ void __launch_bounds__(256) k_bswap_words(uint32_t* __restrict__ words, long long nw) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) words[i] = __byte_perm(words[i], 0u, 0x0123);
+}
+
+__global__ void __launch_bounds__(256) k_fixed_pack(const uint32_t* __restrict__ index, long long count, int b,
+                                                    uint32_t* __restrict__ words) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  ull pattern = (ull)(__brev(index[i]) >> (32 - b));  // LSB first (BIO:41-53)
+  put_bits(words, (ull)i * (ull)b, pattern, b);
+}
+
+__global__ void __launch_bounds__(256) k_fixed_unpack(const uint8_t* __restrict__ bits, long long count, int b,
+                                                      uint32_t* __restrict__ index) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  ull p = (ull)i * (ull)b;
+  uint32_t v = 0;
+  for (int t = 0; t < b; ++t, ++p) v |= (uint32_t)((bits[p >> 3] >> (7 - (int)(p & 7))) & 1u) << t;
+  index[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// the candidate stream, materialised (debug / oracle injection)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_draw(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, float* __restrict__ out) {
+  const uint32_t nq = (G + 3) >> 2;
+  ull t = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (ull)nk * nq) return;
+  uint32_t r = (uint32_t)(t / nq), q = (uint32_t)(t - (ull)r * nq);
+  float z[4];
+  normal_quad(sseed, k0 + r, q, z);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (4 * q + j < G) out[(ull)r * G + 4 * q + j] = z[j];
+}
+
+__global__ void __launch_bounds__(256) k_stream_words(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* __restrict__ out) {
+  ull t = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (ull)nk * nq) return;
+  uint32_t r = (uint32_t)(t / nq), q = (uint32_t)(t - (ull)r * nq);
+  uint32_t o[4];
+  stream_block(sseed, k0 + r, q, o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[t * 4 + j] = o[j];
+}
+
+__global__ void __launch_bounds__(256) k_philox(const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ key,
+                                                uint32_t* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o[4];
+  philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[4 * i + j] = o[j];
+}
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// optional timing of the dominant kernel (k_is_score) with CUDA events on the launching stream
+constexpr int PROFILE_RING = 256;
+static bool g_profile = false;
+static cudaEvent_t g_ev0[PROFILE_RING], g_ev1[PROFILE_RING];
+static int g_profile_count = 0;
+static bool g_profile_events_ready = false;
+
+static int g_sm_count = 0, g_is_blocks_per_sm = 0;
+static int ensure_device_props() {
+  if (g_sm_count > 0) return CWQ_OK;
+  int dev = 0;
+  CWQ_CUDA(cudaGetDevice(&dev));
+  int sms = 0, bps = 0;
+  CWQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score, IS_THREADS, 0));
+  g_is_blocks_per_sm = bps > 0 ? bps : 1;
+  g_sm_count = sms;
+  return CWQ_OK;
+}
+
+}  // namespace cwq
+
+using namespace cwq;
+
+extern "C" int cwq_abi_version(void) { return CWQ_ABI_VERSION; }
+extern "C" const char* cwq_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int cwq_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+  int v = 0;
+  if (sm_count) { CWQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); *sm_count = v; }
+  if (cc_major) { CWQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device)); *cc_major = v; }
+  if (cc_minor) { CWQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device)); *cc_minor = v; }
+  if (clock_khz) { CWQ_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); *clock_khz = v; }
+  return CWQ_OK;
+}
+
+extern "C" long long cwq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int cwq_profile_enable(int on) {
+  if (on && !g_profile_events_ready) {
+    for (int i = 0; i < PROFILE_RING; ++i) { CWQ_CUDA(cudaEventCreate(&g_ev0[i])); CWQ_CUDA(cudaEventCreate(&g_ev1[i])); }
+    g_profile_events_ready = true;
+  }
+  g_profile = on != 0;
+  g_profile_count = 0;
+  return CWQ_OK;
+}
+extern "C" int cwq_profile_count(void) { return g_profile_count; }
+extern "C" int cwq_profile_get_ms(int i, float* ms) {
+  CWQ_REQUIRE(i >= 0 && i < g_profile_count && ms, "no such profile record");
+  CWQ_CUDA(cudaEventElapsedTime(ms, g_ev0[i], g_ev1[i]));
+  return CWQ_OK;
+}
+
+extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
+  if (n_groups < 0) n_groups = 0;
+  size_t b = 0;
+  b += align_up(((size_t)n_groups + 1) * 8);             // unit_off
+  b += align_up((size_t)n_groups * 8);                   // keys
+  b += align_up((size_t)scan_tiles(n_groups + 1) * 8);   // scan tile sums
+  return b + 1024;
+}
+
+extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
+                             int64_t n_groups, int64_t g0, int64_t g1, uint32_t* index, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
+  if (g0 == g1) return CWQ_OK;
+  int rc = ensure_device_props();
+  if (rc != CWQ_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long ng = g1 - g0;
+  Workspace ws(workspace, workspace_bytes);
+  ull* unit_off = ws.take<ull>((size_t)ng + 1);
+  ull* keys = ws.take<ull>((size_t)n_groups);
+  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(ng));
+  ull* total = ws.take<ull>(1);
+  ull* counter = ws.take<ull>(1);
+  if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
+  UnitCount in{K, g0};
+  UnitDeliver out{unit_off, keys, g0};
+  CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, ng, tile_sums, total, st)));
+  k_units_finish<<<1, 32, 0, st>>>(unit_off, ng, total, counter);
+  CWQ_LAUNCH_CHECK();
+  const bool prof = g_profile && g_profile_count < PROFILE_RING;
+  if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
+  k_is_score<<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K, group_seed,
+                                                                     g0, ng, unit_off, counter, keys);
+  CWQ_LAUNCH_CHECK();
+  if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
+  k_is_index<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(keys, g0, g1, index);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,
+                             int64_t n, const float* p_loc, const float* p_scale, float* sample, void* stream) {
+  CWQ_REQUIRE(n > 0, "n must be positive");
+  k_is_decode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)starts, group_seed, gid, index, n,
+                                                                            p_loc, p_scale, sample);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" size_t cwq_outlier_workspace_bytes(int64_t n) {
+  if (n < 0) n = 0;
+  return align_up((size_t)scan_tiles(n) * 4) + 4096 + (1 << 22);  // tile sums + per-segment counters (<= 2^20 segments)
+}
+
+extern "C" int cwq_outlier_encode(const float* q_loc, const float* q_scale, const uint8_t* mask, int64_t n,
+                                  const cwq_segment* segments, int32_t n_segments, float* sample, int64_t* outlier_idx,
+                                  uint16_t* outlier_q, int64_t* seg_outlier_off, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  CWQ_REQUIRE(n > 0 && n_segments > 0 && n_segments <= 1 << 20, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  uint32_t* tile_sums = ws.take<uint32_t>((size_t)scan_tiles(n));
+  unsigned int* counts = ws.take<unsigned int>((size_t)n_segments);
+  if (!tile_sums || !counts) { set_error("cwq_outlier_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
+  CWQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * (size_t)n_segments, st));
+  k_seg_outlier_count<<<n_segments, 256, 0, st>>>(mask, segments, n_segments, counts);
+  CWQ_LAUNCH_CHECK();
+  k_seg_outlier_offsets<<<1, 32, 0, st>>>(counts, n_segments, (long long*)seg_outlier_off);
+  CWQ_LAUNCH_CHECK();
+  OutlierCount in{mask};
+  OutlierDeliver out{mask, q_loc, q_scale, segments, n_segments, sample, (long long*)outlier_idx, outlier_q,
+                     (long long*)seg_outlier_off};
+  CWQ_CUDA((device_exclusive_scan<uint32_t, OutlierCount, OutlierDeliver>(in, out, n, tile_sums, nullptr, st)));
+  return CWQ_OK;
+}
+
+extern "C" int cwq_outlier_decode(float* sample, const int64_t* outlier_pos, const uint16_t* outlier_q, int64_t m,
+                                  void* stream) {
+  if (m <= 0) return CWQ_OK;
+  k_outlier_decode<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, (const long long*)outlier_pos, outlier_q, m);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, const uint32_t* group_seed, int64_t n_groups,
+                                 int64_t g0, int64_t g1, int32_t n_steps, int32_t n_bits_per_step, float shard_scale,
+                                 int64_t max_group_size, uint32_t* indices, float* best, void* stream) {
+  CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
+  CWQ_REQUIRE(n_steps > 0 && n_bits_per_step >= 0 && n_bits_per_step <= 30, "bad step parameters");
+  CWQ_REQUIRE(max_group_size >= 0, "bad max_group_size");
+  if (g0 == g1) return CWQ_OK;
+  size_t gp = (size_t)((max_group_size + 3) / 4 * 4);
+  size_t smem = gp * (sizeof(float2) + sizeof(float));
+  CWQ_REQUIRE(smem <= 200 * 1024, "group too large for shared memory (max_group_size_bits too high)");
+  if (smem > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_greedy_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_greedy_encode<<<(unsigned)(g1 - g0), GREEDY_THREADS, smem, (cudaStream_t)stream>>>(
+      (const float2*)tparam, (const long long*)starts, group_seed, g0, n_steps, 1u << n_bits_per_step, shard_scale, indices, best);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_greedy_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid,
+                                 const uint32_t* indices, int64_t n, int32_t n_steps, float shard_scale,
+                                 const float* p_loc, const float* p_scale, float* sample, void* stream) {
+  CWQ_REQUIRE(n > 0 && n_steps > 0, "bad sizes");
+  k_greedy_decode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)starts, group_seed, gid, indices,
+                                                                                n, n_steps, shard_scale, p_loc, p_scale, sample);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_unrescale(const float* best, const float* p_loc, const float* p_scale, int64_t n, float* sample,
+                             void* stream) {
+  CWQ_REQUIRE(n > 0, "n must be positive");
+  k_unrescale<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(best, p_loc, p_scale, n, sample);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" size_t cwq_pack_workspace_bytes(int64_t n_groups) {
+  if (n_groups < 0) n_groups = 0;
+  return align_up((size_t)scan_tiles(n_groups) * 8) + 1024;
+}
+
+extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, uint8_t* bits, size_t bits_capacity_bytes,
+                                    int64_t* bit_off, void* workspace, size_t workspace_bytes, void* stream) {
+  CWQ_REQUIRE(n_groups > 0, "n_groups must be positive");
+  CWQ_REQUIRE(bits_capacity_bytes % 4 == 0 && bits_capacity_bytes >= ((size_t)n_groups * 42 + 31) / 32 * 4,
+              "bits capacity must be a multiple of 4 and hold 42 bits per group");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(n_groups));
+  ull* total = ws.take<ull>(1);
+  if (!tile_sums || !total) { set_error("cwq_elias_delta_pack: workspace too small"); return CWQ_ERR_WORKSPACE; }
+  CWQ_CUDA(cudaMemsetAsync(bits, 0, bits_capacity_bytes, st));
+  EliasLen in{index};
+  EliasDeliver out{index, (long long*)bit_off, (uint32_t*)bits};
+  CWQ_CUDA((device_exclusive_scan<ull, EliasLen, EliasDeliver>(in, out, n_groups, tile_sums, total, st)));
+  k_bits_finish<<<1, 32, 0, st>>>((long long*)bit_off, n_groups, total);
+  CWQ_LAUNCH_CHECK();
+  long long nw = (long long)(bits_capacity_bytes / 4);
+  k_bswap_words<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((uint32_t*)bits, nw);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_fixed_pack(const uint32_t* index, int64_t count, int32_t bits_per_index, uint8_t* bits,
+                              size_t bits_capacity_bytes, void* stream) {
+  CWQ_REQUIRE(count > 0 && bits_per_index >= 1 && bits_per_index <= 32, "bad sizes");
+  CWQ_REQUIRE(bits_capacity_bytes % 4 == 0 && bits_capacity_bytes * 8 >= (size_t)count * (size_t)bits_per_index,
+              "bits capacity must be a multiple of 4 and hold count * bits_per_index bits");
+  cudaStream_t st = (cudaStream_t)stream;
+  CWQ_CUDA(cudaMemsetAsync(bits, 0, bits_capacity_bytes, st));
+  k_fixed_pack<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(index, count, bits_per_index, (uint32_t*)bits);
+  CWQ_LAUNCH_CHECK();
+  long long nw = (long long)(bits_capacity_bytes / 4);
+  k_bswap_words<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((uint32_t*)bits, nw);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_fixed_unpack(const uint8_t* bits, int64_t count, int32_t bits_per_index, uint32_t* index, void* stream) {
+  CWQ_REQUIRE(count > 0 && bits_per_index >= 1 && bits_per_index <= 32, "bad sizes");
+  k_fixed_unpack<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, count, bits_per_index, index);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_elias_delta_parse_host(const uint8_t* h_ascii_bits, int64_t n_bits, int64_t n_codes, uint32_t* h_index,
+                                          int64_t* h_bits_consumed) {
+  CWQ_REQUIRE(h_ascii_bits && h_index && n_bits >= 0 && n_codes >= 0, "bad arguments");
+  int64_t p = 0;
+  for (int64_t c = 0; c < n_codes; ++c) {
+    int l = 0;
+    while (p < n_bits && h_ascii_bits[p] == '0') { ++l; ++p; }   // BIO:28-29
+    CWQ_REQUIRE(l <= 5 && p + l + 1 <= n_bits, "truncated or malformed Elias-delta stream");
+    uint32_t n_plus_one = 0;
+    for (int t = 0; t <= l; ++t) n_plus_one = (n_plus_one << 1) | (uint32_t)(h_ascii_bits[p++] == '1');   // BIO:33
+    CWQ_REQUIRE(n_plus_one >= 1 && n_plus_one <= 32 && p + (int64_t)n_plus_one - 1 <= n_bits, "truncated or malformed Elias-delta stream");
+    uint64_t x = 1;
+    for (uint32_t t = 0; t + 1 < n_plus_one; ++t) x = (x << 1) | (uint64_t)(h_ascii_bits[p++] == '1');     // BIO:37
+    h_index[c] = (uint32_t)(x - 1);
+  }
+  if (h_bits_consumed) *h_bits_consumed = p;
+  return CWQ_OK;
+}
+
+extern "C" int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, float* out, void* stream) {
+  if (nk == 0 || G == 0) return CWQ_OK;
+  ull t = (ull)nk * ((G + 3) / 4);
+  CWQ_REQUIRE(t < (1ull << 39), "too many draws for one call");
+  k_draw<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stream_seed, k0, nk, G, out);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_stream_words(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out, void* stream) {
+  if (nk == 0 || nq == 0) return CWQ_OK;
+  ull t = (ull)nk * nq;
+  CWQ_REQUIRE(t < (1ull << 39), "too many blocks for one call");
+  k_stream_words<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stream_seed, k0, nk, nq, out);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n, void* stream) {
+  if (n <= 0) return CWQ_OK;
+  k_philox<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctr, key, out, n);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}

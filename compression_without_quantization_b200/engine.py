@@ -1,0 +1,405 @@
+"""Host-side engine: sequences the libcwq.so stages for one or many reference calls ("segments").
+
+PyTorch is used only for device memory, streams and (in distributed.py) torch.distributed; all
+arithmetic happens in the CUDA kernels behind the C ABI (include/cwq.h).  The stage order follows
+the reference's grouped functions:
+
+    importance sampler (CIS:112-274)   prologue -> group -> totals -> encode -> decode -> outliers -> pack
+    greedy sampler     (CGS:170-296)   prologue -> group -> encode -> unrescale -> pack
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CwqError, Segment
+
+
+# ----------------------------------------------------------------------------------------------
+# small helpers
+# ----------------------------------------------------------------------------------------------
+def cuda_device():
+    if not torch.cuda.is_available():
+        raise CwqError("no CUDA device visible: the engine has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def is_float32(dtype):
+    """True for numpy / torch / TF-style float32 dtype objects (the reference tests `is tf.float32`)."""
+    if dtype is None:
+        return False
+    if dtype is torch.float32:
+        return True
+    try:
+        return np.dtype(dtype) == np.float32
+    except TypeError:
+        pass
+    name = getattr(dtype, "name", None) or str(dtype)
+    return name in ("float32", "<dtype: 'float32'>", "torch.float32")
+
+
+def as_device_f32(x, device=None, what="array"):
+    """Flat contiguous float32 CUDA tensor from numpy / torch / any DLPack producer (zero-copy when the
+    data already lives on the device)."""
+    device = device or cuda_device()
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        if x.dtype != np.float32:
+            raise Exception("{} datatype must be float32!".format(what))
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    elif hasattr(x, "numpy"):
+        t = torch.from_numpy(np.ascontiguousarray(x.numpy()))
+    else:
+        a = np.asarray(x)
+        if a.dtype != np.float32:
+            raise Exception("{} datatype must be float32!".format(what))
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype != torch.float32:
+        raise Exception("{} datatype must be float32!".format(what))
+    return t.to(device, non_blocking=True).reshape(-1).contiguous()
+
+
+def size_limit(max_group_size_bits, strict):
+    """Running group size at which the reference's size test fires: CIS:185-187 evaluates
+    ``np.log(size + 1) / np.log(2) > max_group_size_bits`` (CGS:230-232: ``>=``); the same expression is
+    evaluated here around 2**bits so the kernels can compare integers."""
+    m = max_group_size_bits
+    guess = int(np.floor(2.0 ** float(m)))
+    for size in range(max(0, guess - 3), guess + 4):
+        bits = np.log(size + 1) / np.log(2)
+        if (bits > m) if strict else (bits >= m):
+            return size
+    raise CwqError("cannot bracket the group size limit for max_group_size_bits={}".format(m))
+
+
+@dataclass
+class SegmentSpec:
+    """One reference call: a flat latent vector of n dims with its own parameters."""
+    n: int
+    seed: int
+    n_bits_per_group: float
+    max_group_size_bits: float
+    dim_kl_bit_limit: float = float("inf")
+    strict: bool = True  # True: importance sampler ('>'), False: greedy ('>=')
+
+
+class SegmentTable:
+    def __init__(self, specs, device):
+        self.specs = list(specs)
+        self.count = len(self.specs)
+        if self.count == 0:
+            raise CwqError("at least one segment is required")
+        self.host = (Segment * self.count)()
+        off = 0
+        for i, sp in enumerate(self.specs):
+            if sp.n <= 0:
+                raise CwqError("segments must be non-empty")
+            n_nats = sp.n_bits_per_group * np.log(2) - 1  # CIS:181 / CGS:226, float64
+            self.host[i] = Segment(off, off + sp.n, float(n_nats), size_limit(sp.max_group_size_bits, sp.strict),
+                                   float(sp.dim_kl_bit_limit), int(sp.seed) & 0xFFFFFFFF, 1 if sp.strict else 0, 0)
+            off += sp.n
+        self.n = off
+        self.starts = [int(s.start) for s in self.host]
+        self.dev = torch.frombuffer(bytearray(bytes(self.host)), dtype=torch.uint8).to(device)
+        self.max_size_limit = max(int(s.size_limit) for s in self.host)
+
+
+class _Groups:
+    """Group tables on the device (+ the per-segment offsets on the host)."""
+
+    def __init__(self, starts, group_seed, gid, seg_group_off, seg_group_off_host):
+        self.starts = starts
+        self.group_seed = group_seed
+        self.gid = gid
+        self.seg_group_off = seg_group_off
+        self.seg_group_off_host = seg_group_off_host
+        self.n_groups = int(seg_group_off_host[-1])
+
+
+def _run_group(kl, table):
+    dev = kl.device
+    n, ns = table.n, table.count
+    starts = torch.empty(n + ns + 1, dtype=torch.int64, device=dev)
+    group_seed = torch.empty(n + ns, dtype=torch.int32, device=dev)
+    gid = torch.empty(n, dtype=torch.int32, device=dev)
+    seg_off = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+    wsb = _lib.load().cwq_group_workspace_bytes(n, ns)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    _lib.call("cwq_group", _ptr(kl), n, _ptr(table.dev), ctypes.cast(table.host, ctypes.c_void_p), ns, _ptr(starts),
+              _ptr(group_seed), _ptr(gid), _ptr(seg_off), _ptr(ws), wsb, _stream())
+    seg_off_host = seg_off.cpu().numpy()  # the one mid-pipeline host sync: n_groups sizes everything after
+    ng = int(seg_off_host[-1])
+    return _Groups(starts[:ng + 1], group_seed[:ng], gid, seg_off, seg_off_host)
+
+
+def _forced_groups(starts_host_per_segment, table, device):
+    """Group tables from caller-supplied starts (decoder side / per-group entry points)."""
+    flat = []
+    seg_off = [0]
+    for s, st in enumerate(starts_host_per_segment):
+        st = np.asarray(st, dtype=np.int64).reshape(-1)
+        if st.size < 2 or st[0] != 0 or st[-1] != table.specs[s].n or np.any(np.diff(st) < 0):
+            raise CwqError("group_start_indices must start at 0, end at the number of dimensions and be sorted")
+        flat.append(st[:-1] + table.starts[s])
+        seg_off.append(seg_off[-1] + st.size - 1)
+    flat.append(np.array([table.n], dtype=np.int64))
+    starts = torch.from_numpy(np.concatenate(flat)).to(device)
+    seg_off_host = np.asarray(seg_off, dtype=np.int64)
+    seg_off_dev = torch.from_numpy(seg_off_host).to(device)
+    ng = int(seg_off_host[-1])
+    gid = torch.empty(table.n, dtype=torch.int32, device=device)
+    group_seed = torch.empty(ng, dtype=torch.int32, device=device)
+    _lib.call("cwq_expand_groups", _ptr(starts), ng, table.n, _ptr(table.dev), table.count, _ptr(seg_off_dev), _ptr(gid),
+              _ptr(group_seed), _stream())
+    return _Groups(starts, group_seed, gid, seg_off_dev, seg_off_host)
+
+
+def bits_to_ascii(bits_host, n_bits, bit_begin=0):
+    """Packed MSB-first bits -> the reference's '0'/'1' byte string (BIO:76-79 in reverse)."""
+    if n_bits == 0:
+        return b""
+    b0 = bit_begin // 8
+    b1 = (bit_begin + n_bits + 7) // 8
+    u = np.unpackbits(bits_host[b0:b1])
+    lo = bit_begin - 8 * b0
+    return (u[lo:lo + n_bits] + np.uint8(48)).tobytes()
+
+
+def ascii_to_bits(code):
+    """'0'/'1' str or bytes -> (packed MSB-first uint8 array, number of bits)."""
+    if isinstance(code, str):
+        code = code.encode("utf-8")
+    a = np.frombuffer(code, dtype=np.uint8)
+    if a.size and (a.min() < 48 or a.max() > 49):
+        raise CwqError("bitcode must consist of '0' and '1' characters")
+    return np.packbits(a - np.uint8(48)), a.size
+
+
+# ----------------------------------------------------------------------------------------------
+# importance sampler
+# ----------------------------------------------------------------------------------------------
+class ISJob:
+    """Stages of the grouped importance sampler over a batch of segments (device-resident)."""
+
+    def __init__(self, q_loc, q_scale, p_loc, p_scale, specs, forced_starts=None):
+        self.dev = q_loc.device
+        self.q_loc, self.q_scale, self.p_loc, self.p_scale = q_loc, q_scale, p_loc, p_scale
+        self.table = SegmentTable(specs, self.dev)
+        self.n = self.table.n
+        if not (q_loc.numel() == q_scale.numel() == p_loc.numel() == p_scale.numel() == self.n):
+            raise CwqError("loc/scale arrays must all have {} elements".format(self.n))
+        self.forced_starts = forced_starts
+        self.groups = None
+
+    def prepare(self):
+        n, t = self.n, self.table
+        self.kl = torch.empty(n, dtype=torch.float32, device=self.dev)
+        self.coef = torch.empty(2 * n, dtype=torch.float32, device=self.dev)
+        self.mask = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_is_prologue", _ptr(self.q_loc), _ptr(self.q_scale), _ptr(self.p_loc), _ptr(self.p_scale), n,
+                  _ptr(t.dev), t.count, _ptr(self.kl), _ptr(self.coef), _ptr(self.mask), _stream())
+        if self.forced_starts is None:
+            self.groups = _run_group(self.kl, t)
+        else:
+            self.groups = _forced_groups(self.forced_starts, t, self.dev)
+        ng = self.groups.n_groups
+        self.total_kl = torch.empty(ng, dtype=torch.float32, device=self.dev)
+        self.K = torch.empty(ng, dtype=torch.int32, device=self.dev)
+        _lib.call("cwq_group_totals", _ptr(self.kl), _ptr(self.groups.starts), ng, _ptr(self.total_kl), _ptr(self.K),
+                  _stream())
+        self.index = torch.zeros(ng, dtype=torch.int32, device=self.dev)  # uint32 payload
+        return self
+
+    def encode(self, g0=0, g1=None):
+        ng = self.groups.n_groups
+        g1 = ng if g1 is None else g1
+        wsb = _lib.load().cwq_is_encode_workspace_bytes(ng)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_is_encode", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
+                  ng, g0, g1, _ptr(self.index), _ptr(ws), wsb, _stream())
+        return self
+
+    def decode(self):
+        """Regenerate the chosen rows (un-rescaled) and overwrite outlier dims; fills the side information."""
+        n, t, g = self.n, self.table, self.groups
+        self.sample = torch.empty(n, dtype=torch.float32, device=self.dev)
+        _lib.call("cwq_is_decode", _ptr(g.starts), _ptr(g.group_seed), _ptr(g.gid), _ptr(self.index), n, _ptr(self.p_loc),
+                  _ptr(self.p_scale), _ptr(self.sample), _stream())
+        n_out_cap = n
+        self.outlier_idx = torch.empty(n_out_cap, dtype=torch.int64, device=self.dev)
+        self.outlier_q = torch.empty(n_out_cap, dtype=torch.int16, device=self.dev)  # uint16 payload
+        self.seg_outlier_off = torch.empty(t.count + 1, dtype=torch.int64, device=self.dev)
+        wsb = _lib.load().cwq_outlier_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_outlier_encode", _ptr(self.q_loc), _ptr(self.q_scale), _ptr(self.mask), n, _ptr(t.dev), t.count,
+                  _ptr(self.sample), _ptr(self.outlier_idx), _ptr(self.outlier_q), _ptr(self.seg_outlier_off), _ptr(ws),
+                  wsb, _stream())
+        return self
+
+    def pack(self):
+        ng = self.groups.n_groups
+        cap = ((ng * 42 + 31) // 32) * 4
+        self.bits = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+        self.bit_off = torch.empty(ng + 1, dtype=torch.int64, device=self.dev)
+        wsb = _lib.load().cwq_pack_workspace_bytes(ng)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_elias_delta_pack", _ptr(self.index), ng, _ptr(self.bits), cap, _ptr(self.bit_off), _ptr(ws), wsb,
+                  _stream())
+        return self
+
+    # ---- host views (each does a device->host copy) ----
+    def segment_group_range(self, s):
+        off = self.groups.seg_group_off_host
+        return int(off[s]), int(off[s + 1])
+
+    def host_starts(self, s):
+        g0, g1 = self.segment_group_range(s)
+        return (self.groups.starts[g0:g1 + 1] - self.table.starts[s]).cpu().numpy()
+
+    def host_indices(self, s):
+        g0, g1 = self.segment_group_range(s)
+        return self.index[g0:g1].cpu().numpy().view(np.uint32)
+
+
+# ----------------------------------------------------------------------------------------------
+# greedy sampler
+# ----------------------------------------------------------------------------------------------
+def greedy_shard_scale(rho, n_steps):
+    """CGS:42-45 with p = N(0,1): f32(rho) / f32(sqrt(n_steps))."""
+    return float(np.float32(rho) / np.float32(np.sqrt(n_steps)))
+
+
+class GreedyJob:
+    def __init__(self, q_loc, q_scale, p_loc, p_scale, specs, n_steps, n_bits_per_step, rho=1.0, forced_starts=None):
+        self.dev = q_loc.device
+        self.q_loc, self.q_scale, self.p_loc, self.p_scale = q_loc, q_scale, p_loc, p_scale
+        self.table = SegmentTable(specs, self.dev)
+        self.n = self.table.n
+        if not (q_loc.numel() == q_scale.numel() == p_loc.numel() == p_scale.numel() == self.n):
+            raise CwqError("loc/scale arrays must all have {} elements".format(self.n))
+        self.n_steps, self.n_bits_per_step = int(n_steps), int(n_bits_per_step)
+        if self.n_steps <= 0 or not (0 <= self.n_bits_per_step <= 30):
+            raise CwqError("n_steps must be positive and 0 <= n_bits_per_step <= 30")
+        self.shard_scale = greedy_shard_scale(rho, n_steps)
+        self.forced_starts = forced_starts
+
+    def prepare(self):
+        n = self.n
+        self.kl = torch.empty(n, dtype=torch.float32, device=self.dev)
+        self.tparam = torch.empty(2 * n, dtype=torch.float32, device=self.dev)
+        _lib.call("cwq_greedy_prologue", _ptr(self.q_loc), _ptr(self.q_scale), _ptr(self.p_loc), _ptr(self.p_scale), n,
+                  _ptr(self.kl), _ptr(self.tparam), _stream())
+        if self.forced_starts is None:
+            self.groups = _run_group(self.kl, self.table)
+        else:
+            self.groups = _forced_groups(self.forced_starts, self.table, self.dev)
+        ng = self.groups.n_groups
+        self.indices = torch.zeros(ng * self.n_steps, dtype=torch.int32, device=self.dev)
+        self.best = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        sizes = self.groups.starts[1:] - self.groups.starts[:-1]
+        self.max_group_size = int(sizes.max().item())
+        return self
+
+    def encode(self, g0=0, g1=None):
+        ng = self.groups.n_groups
+        g1 = ng if g1 is None else g1
+        _lib.call("cwq_greedy_encode", _ptr(self.tparam), _ptr(self.groups.starts), _ptr(self.groups.group_seed), ng, g0, g1,
+                  self.n_steps, self.n_bits_per_step, self.shard_scale, self.max_group_size, _ptr(self.indices),
+                  _ptr(self.best), _stream())
+        return self
+
+    def decode(self):
+        """Replay the chosen rows from the indices (what the decoder runs), un-rescaled."""
+        g = self.groups
+        self.sample = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+        _lib.call("cwq_greedy_decode", _ptr(g.starts), _ptr(g.group_seed), _ptr(g.gid), _ptr(self.indices), self.n,
+                  self.n_steps, self.shard_scale, _ptr(self.p_loc), _ptr(self.p_scale), _ptr(self.sample), _stream())
+        return self
+
+    def unrescale(self):
+        if getattr(self, "best_from_decode", False):
+            return self  # sharded run: the sample was already rebuilt from the gathered indices (decode())
+        self.sample = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+        _lib.call("cwq_unrescale", _ptr(self.best), _ptr(self.p_loc), _ptr(self.p_scale), self.n, _ptr(self.sample), _stream())
+        return self
+
+    def pack(self):
+        count = self.groups.n_groups * self.n_steps
+        b = self.n_bits_per_step
+        if b == 0 or count == 0:
+            self.bits = torch.zeros(4, dtype=torch.uint8, device=self.dev)
+            return self
+        cap = ((count * b + 31) // 32) * 4
+        self.bits = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_fixed_pack", _ptr(self.indices), count, b, _ptr(self.bits), cap, _stream())
+        return self
+
+    def segment_group_range(self, s):
+        off = self.groups.seg_group_off_host
+        return int(off[s]), int(off[s + 1])
+
+    def host_starts(self, s):
+        g0, g1 = self.segment_group_range(s)
+        return (self.groups.starts[g0:g1 + 1] - self.table.starts[s]).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# the candidate stream (misc.py:3-17)
+# ----------------------------------------------------------------------------------------------
+def draw_candidates(stream_seed, k0, nk, G, device=None):
+    """Rows k0..k0+nk-1 of the N(0,1) table of stream `stream_seed` as a float32 [nk, G] CUDA tensor."""
+    device = device or cuda_device()
+    out = torch.empty((int(nk), int(G)), dtype=torch.float32, device=device)
+    if nk and G:
+        _lib.call("cwq_draw_candidates", int(stream_seed) & 0xFFFFFFFF, int(k0) & 0xFFFFFFFF, int(nk), int(G), _ptr(out),
+                  _stream())
+    return out
+
+
+def stream_words(stream_seed, k0, nk, nq, device=None):
+    device = device or cuda_device()
+    out = torch.empty((int(nk), int(nq), 4), dtype=torch.int32, device=device)
+    if nk and nq:
+        _lib.call("cwq_stream_words", int(stream_seed) & 0xFFFFFFFF, int(k0) & 0xFFFFFFFF, int(nk), int(nq), _ptr(out),
+                  _stream())
+    return out
+
+
+def philox4x32_10(ctr, key, device=None):
+    """ctr uint32[n,4], key uint32[n,2] (numpy) -> uint32[n,4] (numpy)."""
+    device = device or cuda_device()
+    c = torch.from_numpy(np.ascontiguousarray(ctr, dtype=np.uint32).view(np.int32)).to(device)
+    k = torch.from_numpy(np.ascontiguousarray(key, dtype=np.uint32).view(np.int32)).to(device)
+    n = c.numel() // 4
+    out = torch.empty_like(c)
+    _lib.call("cwq_philox4x32_10", _ptr(c), _ptr(k), _ptr(out), n, _stream())
+    return out.cpu().numpy().view(np.uint32).reshape(-1, 4)
+
+
+def elias_delta_parse(code, n_codes):
+    """Sequential parse of n_codes Elias-delta codes from a '0'/'1' str/bytes -> (uint32 indices (x - 1), bits used)."""
+    if isinstance(code, str):
+        code = code.encode("utf-8")
+    if int(n_codes) == 0:
+        return np.zeros(0, dtype=np.uint32), 0
+    buf = np.frombuffer(code, dtype=np.uint8)
+    if buf.size == 0:
+        raise CwqError("empty bitcode for {} groups".format(n_codes))
+    out = np.empty(max(int(n_codes), 1), dtype=np.uint32)
+    used = ctypes.c_int64(0)
+    _lib.call("cwq_elias_delta_parse_host", ctypes.c_void_p(buf.ctypes.data if buf.size else 0), int(buf.size), int(n_codes),
+              ctypes.c_void_p(out.ctypes.data), ctypes.cast(ctypes.pointer(used), ctypes.c_void_p))
+    return out[:int(n_codes)], int(used.value)

@@ -1,0 +1,186 @@
+// Pipe-throughput microbenchmarks for the MIRACLE candidate loop on sm_100a.
+// Confirms the denominators SURVEY.md section 8(d) carried over from Hopper documentation:
+// FP32 lanes/clk/SM, IMAD.WIDE rate, LOP3 rate, MUFU rate, and the cost of a whole
+// Philox4x32-10 block / Box-Muller pair.  Stand-alone: nvcc -O3 -arch=sm_100a pipes.cu -o pipes
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
+  fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
+
+constexpr int ITERS = 4096;
+constexpr int U = 8;  // independent chains per thread
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_pipe(uint32_t* out, uint32_t seed, long long* cyc) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  float f[U]; uint32_t u[U]; uint32_t v[U];
+#pragma unroll
+  for (int i = 0; i < U; ++i) { f[i] = 1.0f + 1e-3f * (float)((tid + i) & 1023); u[i] = tid * 2654435761u + i + seed; v[i] = u[i] ^ 0x9E3779B9u; }
+  float c1 = 1.0f + 1e-7f * (float)seed, c2 = 1e-9f * (float)seed;
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      if (OP == 0) f[i] = __fmaf_rn(f[i], c1, c2);                               // FFMA
+      if (OP == 1) { u[i] = u[i] ^ v[i] ^ seed; v[i] = (v[i] & u[i]) ^ seed; }   // 2x LOP3
+      if (OP == 2) { unsigned long long w = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (uint32_t)(w >> 32) ^ (uint32_t)w; }  // IMAD.WIDE + LOP
+      if (OP == 3) u[i] = __umulhi(u[i], 0xD2511F53u) + 1;                        // IMAD.HI
+      if (OP == 4) u[i] = u[i] * 0xD2511F53u + 1;                                // IMAD lo
+      if (OP == 5) f[i] = __log2f(f[i]) + 2.0f;                                  // MUFU.LG2 (+FADD)
+      if (OP == 6) f[i] = __sinf(f[i]);                                          // FMUL + MUFU.SIN
+      if (OP == 7) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f[i])); f[i] = r + 1.0f; }
+      if (OP == 8) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f[i])); f[i] = r + 1.0f; }
+      if (OP == 9) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f[i])); f[i] = r * 0.25f; }
+      if (OP == 10) { // fma.rn.f32x2 : two fp32 FMAs in one instruction (sm_100+)
+        unsigned long long a, b, c, d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(f[i]), "f"(__uint_as_float(u[i] & 0x3fffffffu)));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(c1), "f"(c1));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c2), "f"(c2));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+        float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+        f[i] = lo; u[i] = __float_as_uint(hi);
+      }
+      if (OP == 11) { f[i] = __fmaf_rn(f[i], c1, c2); u[i] = u[i] ^ v[i] ^ seed; }   // FFMA + LOP3 dual-pipe
+      if (OP == 12) { unsigned long long w = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (uint32_t)(w >> 32) ^ (uint32_t)w; f[i] = __fmaf_rn(f[i], c1, c2); } // IMAD.WIDE + LOP + FFMA
+      if (OP == 13) { f[i] = __cosf(f[i]) + 1.5f; }
+      if (OP == 14) { u[i] = __float_as_uint((float)u[i]) + 3u; }                // I2F
+    }
+  }
+  long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < U; ++i) acc ^= __float_as_uint(f[i]) ^ u[i] ^ v[i];
+  if (acc == 0x12345u) out[tid & 1023] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// ---- composite: Philox4x32-10 block, counter (k, q, 0, 0), key (s, 42) ----
+__device__ __forceinline__ void philox_block(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
+  uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned long long p0 = (unsigned long long)c0 * 0xD2511F53u;
+    unsigned long long p1 = (unsigned long long)c2 * 0xCD9E8D57u;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
+  float f1 = __uint_as_float((x0 & 0x007fffffu) | 0x3f800000u);   // [1,2)
+  float f2 = __uint_as_float((x1 & 0x007fffffu) | 0x3f800000u);
+  float u1 = 2.0f - f1;                                           // (0,1]
+  float l = __log2f(u1);
+  float r2 = l * -1.3862943611198906f;                            // -2 ln2 * lg2(u)
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+  float th = __fmaf_rn(f2, 6.283185307179586f, -6.283185307179586f);
+  z0 = r * __cosf(th); z1 = r * __sinf(th);
+}
+
+// MODE 0: philox only; 1: philox + box-muller; 2: + IS score with params in registers (G=16)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_comp(uint32_t* out, uint32_t seed, int ncand, const float2* __restrict__ coef, long long* cyc) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float2 sc[16];
+  if (threadIdx.x < 16) sc[threadIdx.x] = coef[threadIdx.x];
+  __syncthreads();
+  float best = -3.0e38f; uint32_t bestk = 0; uint32_t xacc = 0;
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ncand; ++it) {
+    uint32_t k = tid + it * (gridDim.x * blockDim.x);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o[4];
+      philox_block(k, q, seed, 42u, o);
+      if (MODE == 0) { xacc ^= o[0] ^ o[1] ^ o[2] ^ o[3]; }
+      else {
+        float z[4];
+        box_muller(o[0], o[1], z[0], z[1]);
+        box_muller(o[2], o[3], z[2], z[3]);
+        if (MODE == 1) { acc += z[0] + z[1] + z[2] + z[3]; }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { float2 ab = sc[q * 4 + j]; acc = __fmaf_rn(z[j], __fmaf_rn(ab.x, z[j], ab.y), acc); }
+        }
+      }
+    }
+    if (MODE != 0 && acc > best) { best = acc; bestk = k; }
+  }
+  long long t1 = clock64();
+  if ((xacc ^ bestk ^ __float_as_uint(best)) == 0x12345u) out[tid & 1023] = bestk;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+template <int OP>
+void run_pipe(const char* name, double ops_per_iter_per_chain, int sms, uint32_t* d_out, long long* d_cyc, int blocks_per_sm, int threads) {
+  int grid = sms * blocks_per_sm;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  k_pipe<OP><<<grid, threads>>>(d_out, 1, d_cyc);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(a));
+  k_pipe<OP><<<grid, threads>>>(d_out, 1, d_cyc);
+  CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+  float ms; CK(cudaEventElapsedTime(&ms, a, b));
+  long long cyc; CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+  double total = (double)grid * threads * ITERS * U * ops_per_iter_per_chain;
+  double mhz = cyc / (ms * 1e3);
+  printf("%-28s grid=%dx%d  %8.3f ms  cyc(blk0)=%lld (~%.0f MHz)  %.2f ops/clk/SM  %.3e ops/s\n",
+         name, grid, threads, ms, cyc, mhz, total / ((double)cyc * sms), total / (ms * 1e-3));
+}
+
+template <int MODE>
+void run_comp(const char* name, int sms, uint32_t* d_out, long long* d_cyc, const float2* d_coef, int blocks_per_sm) {
+  int grid = sms * blocks_per_sm, threads = 256, ncand = 512;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  k_comp<MODE><<<grid, threads>>>(d_out, 7, ncand, d_coef, d_cyc);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(a));
+  k_comp<MODE><<<grid, threads>>>(d_out, 7, ncand, d_coef, d_cyc);
+  CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+  float ms; CK(cudaEventElapsedTime(&ms, a, b));
+  long long cyc; CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+  double cd = (double)grid * threads * ncand * 16.0;  // candidate-dims
+  printf("%-28s grid=%dx%d  %8.3f ms  cyc(blk0)=%lld (~%.0f MHz)  %.2f cand-dims/clk/SM  %.3e cand-dims/s\n",
+         name, grid, threads, ms, cyc, cyc / (ms * 1e3), cd / ((double)cyc * sms), cd / (ms * 1e-3));
+}
+
+int main() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int sms = p.multiProcessorCount;
+  printf("device: %s  SMs=%d  cc=%d.%d  clockRate=%d kHz  regs/SM=%d smem/SM=%zu\n", p.name, sms, p.major, p.minor, p.clockRate, p.regsPerMultiprocessor, p.sharedMemPerMultiprocessor);
+  uint32_t* d_out; long long* d_cyc; float2* d_coef;
+  CK(cudaMalloc(&d_out, 4096)); CK(cudaMalloc(&d_cyc, 8)); CK(cudaMalloc(&d_coef, 16 * sizeof(float2)));
+  float2 h[16]; for (int i = 0; i < 16; ++i) { h[i].x = -0.5f - 0.1f * i; h[i].y = 0.3f * (i - 8); }
+  CK(cudaMemcpy(d_coef, h, sizeof(h), cudaMemcpyHostToDevice));
+  for (int bps : {4, 8}) {
+    printf("---- blocks/SM = %d (256 thr) ----\n", bps);
+    run_pipe<0>("FFMA", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<10>("FFMA2 (f32x2, counts 2)", 2, sms, d_out, d_cyc, bps, 256);
+    run_pipe<1>("LOP3 x2", 2, sms, d_out, d_cyc, bps, 256);
+    run_pipe<2>("IMAD.WIDE(+LOP)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<3>("IMAD.HI(+IADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<4>("IMAD lo", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<5>("MUFU.LG2(+FADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<6>("MUFU.SIN(+FMUL)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<13>("MUFU.COS(+FMUL,FADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<7>("MUFU.SQRT(+FADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<8>("MUFU.RSQ(+FADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<9>("MUFU.EX2(+FMUL)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<14>("I2F(+IADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<11>("FFMA+LOP3 pair", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<12>("IMAD.WIDE+LOP+FFMA triple", 1, sms, d_out, d_cyc, bps, 256);
+    run_comp<0>("philox only (per 4 u32 = 4cd)", sms, d_out, d_cyc, d_coef, bps);
+    run_comp<1>("philox+boxmuller", sms, d_out, d_cyc, d_coef, bps);
+    run_comp<2>("philox+bm+IS score", sms, d_out, d_cyc, d_coef, bps);
+  }
+  return 0;
+}
