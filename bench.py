@@ -60,6 +60,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -72,7 +73,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
@@ -82,7 +89,8 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.25)]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -165,7 +173,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=24)
@@ -216,6 +224,9 @@ def main():
         return job
 
     # ---- device-resident throughput ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # started before the warm-up so nvidia-smi is already streaming in the timed window
     job = None
     for _ in range(max(args.warmup, 3)):
         job = step_device()
@@ -233,11 +244,9 @@ def main():
 
     lib.cwq_profile_enable(1)
     launches0 = lib.cwq_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.window_begin()
     wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
@@ -245,6 +254,7 @@ def main():
     ev1.record()
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.cwq_launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)

@@ -51,16 +51,22 @@ __device__ __forceinline__ ull warp_max_key(ull key) {
   return key;
 }
 
-// candidates [kb, ke) of one group, NQ quads of coefficients staged in this warp's shared slice
+// candidates [kb, ke) of one group, NQ quads of coefficients staged in this warp's shared slice.
+// Per candidate: 2 shared IMAD.WIDE (lane_shared) + 14 per quad (rounds 3..9); the (seed, q) parts of
+// rounds 1-2 live in registers (qc).
 template <int NQ>
 __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
                                                int lane, float& best, uint32_t& bestk) {
+  QuadConst qc[NQ > 0 ? NQ : 1];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) qc[q] = quad_const(sseed, (uint32_t)q);
   for (uint32_t k = kb + lane; k < ke; k += 32) {
+    const LaneShared ls = lane_shared(sseed, k);
     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       float z[4];
-      normal_quad(sseed, k, (uint32_t)q, z);
+      normal_quad_tail(sseed, ls, qc[q], z);
       float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
       acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
       acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
@@ -77,10 +83,11 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
                                                        uint32_t ke, int lane, float& best, uint32_t& bestk) {
   const int nq = (G + 3) >> 2;
   for (uint32_t k = kb + lane; k < ke; k += 32) {
+    const LaneShared ls = lane_shared(sseed, k);
     float acc0 = 0.0f, acc1 = 0.0f;
     for (int q = 0; q < nq; ++q) {
       float z[4];
-      normal_quad(sseed, k, (uint32_t)q, z);
+      normal_quad_tail(sseed, ls, quad_const(sseed, (uint32_t)q), z);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int d = 4 * q + j;
@@ -246,7 +253,8 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
   const int G = (int)(starts[g + 1] - s);
   const int nq = (G + 3) >> 2, Gp = nq * 4;
   float2* ce = reinterpret_cast<float2*>(smem_raw);            // (c_d, e_d)
-  float* best = reinterpret_cast<float*>(smem_raw + (size_t)Gp * sizeof(float2));
+  uint4* qtab = reinterpret_cast<uint4*>(smem_raw + (size_t)Gp * sizeof(float2));   // (a, b, c3, -) per quad, this step's stream
+  float* best = reinterpret_cast<float*>(smem_raw + (size_t)Gp * sizeof(float2) + (size_t)nq * sizeof(uint4));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t group_seed = gseed[g];
   for (int d = tid; d < Gp; d += GREEDY_THREADS) {
@@ -260,16 +268,24 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
       float2 t = tparam[s + d];
       ce[d].y = __fmul_rn(__fsub_rn(best[d], t.x), t.y);
     }
+    for (int q = tid; q < nq; q += GREEDY_THREADS) {
+      QuadConst c = quad_const(sseed, (uint32_t)q);
+      qtab[q] = make_uint4(c.a, c.b, c.c3, 0u);
+    }
     __syncthreads();
     float bs = __uint_as_float(0x7f800000u);
     uint32_t bk = 0xffffffffu;
     const float4* ce4 = reinterpret_cast<const float4*>(ce);
     for (uint32_t k = tid; k < n_samples; k += GREEDY_THREADS) {
+      const LaneShared ls = lane_shared(sseed, k);
       float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll 2
       for (int q = 0; q < nq; ++q) {
         float z[4];
-        normal_quad(sseed, k, (uint32_t)q, z);
+        const uint4 t = qtab[q];
+        QuadConst qc;
+        qc.a = t.x; qc.b = t.y; qc.c3 = t.z;
+        normal_quad_tail(sseed, ls, qc, z);
         float4 c01 = ce4[2 * q], c23 = ce4[2 * q + 1];
         float u0 = __fmaf_rn(z[0], c01.x, c01.y);
         float u1 = __fmaf_rn(z[1], c01.z, c01.w);
@@ -594,7 +610,7 @@ extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, con
   CWQ_REQUIRE(max_group_size >= 0, "bad max_group_size");
   if (g0 == g1) return CWQ_OK;
   size_t gp = (size_t)((max_group_size + 3) / 4 * 4);
-  size_t smem = gp * (sizeof(float2) + sizeof(float));
+  size_t smem = gp * (sizeof(float2) + sizeof(float)) + gp / 4 * sizeof(uint4);
   CWQ_REQUIRE(smem <= 200 * 1024, "group too large for shared memory (max_group_size_bits too high)");
   if (smem > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_greedy_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_greedy_encode<<<(unsigned)(g1 - g0), GREEDY_THREADS, smem, (cudaStream_t)stream>>>(

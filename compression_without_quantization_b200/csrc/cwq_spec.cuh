@@ -18,26 +18,82 @@ constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t STREAM_KEY1 = 42u;             // reference misc.py:11  seed = [seed, 42]
 constexpr uint32_t OUTLIER_STREAM_OFFSET = 0x9E3779B9u;
 
-// Philox4x32-10, full generality (used by the KAT entry point).
+__device__ __forceinline__ void mulwide_generic(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo) {
+  unsigned long long p = (unsigned long long)a * m;   // plain C: lets the compiler fold constant operands
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+}
+
+// Philox4x32-10, full generality (KAT entry point, decode / draw kernels).
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    unsigned long long p0 = (unsigned long long)PHILOX_M0 * c0;
-    unsigned long long p1 = (unsigned long long)PHILOX_M1 * c2;
-    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
-    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    uint32_t h0, l0, h1, l1;
+    mulwide_generic(c0, PHILOX_M0, h0, l0);
+    mulwide_generic(c2, PHILOX_M1, h1, l1);
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
     k0 += PHILOX_W0; k1 += PHILOX_W1;
   }
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// The candidate stream's block: counter (k, q, 0, 0), key (stream_seed, 42).  With c2 = c3 = 0 the
-// first round's second multiply is a constant and the second round's first multiply depends only on
-// (q, stream_seed), so ptxas hoists it out of the candidate loop: 18 of the 20 multiplies remain.
+// 32 x 32 -> 64 bit multiply as ONE IMAD.WIDE (the C form `(u64)a * m` makes ptxas emit two extra
+// adds per product on sm_100a; measured in tools/microbench/is_loop.cu).
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo) {
+  asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(m));
+}
+
+// The candidate stream's block: counter (0, k, 0, q), key (stream_seed, 42).
+// Why this placement: with c0 = c2 = 0 round 0 needs no multiply, and in rounds 1-2 one product of each
+// pair depends only on (q, seed) -- hoisted out of the candidate loop -- while the other depends only on
+// (k, seed) and is shared by all quads of a candidate.  Only rounds 3..9 cost two IMAD.WIDE per block:
+// 14.5 instead of 20 wide multiplies per block.  IMAD.WIDE (4.25 cycles per warp on the FMA pipe, which
+// FP32 work shares) is the binding resource of the whole path (profiles/r01_pipe_overlap_microbench.log).
 __device__ __forceinline__ void stream_block(uint32_t sseed, uint32_t k, uint32_t q, uint32_t (&o)[4]) {
-  philox4x32_10(k, q, 0u, 0u, sseed, STREAM_KEY1, o);
+  philox4x32_10(0u, k, 0u, q, sseed, STREAM_KEY1, o);
+}
+
+// -- the same block, factored for the hot loops --------------------------------------------------
+// state after round 2 is (h ^ a, l, l0 ^ b, c3) with (a, b, c3) a function of (seed, q) only and
+// (h, l, l0) a function of (seed, k) only.
+struct QuadConst { uint32_t a, b, c3; };
+struct LaneShared { uint32_t h, l, l0; };
+
+__device__ __forceinline__ QuadConst quad_const(uint32_t sseed, uint32_t q) {
+  uint32_t h1, l1, h0, l0;
+  mulwide_generic(q ^ STREAM_KEY1, PHILOX_M1, h1, l1);               // round 1, p1 (constant when q is)
+  mulwide(h1 ^ (sseed + PHILOX_W0), PHILOX_M0, h0, l0);              // round 2, p0
+  QuadConst c;
+  c.a = l1 ^ (sseed + 2u * PHILOX_W0);
+  c.b = h0 ^ (STREAM_KEY1 + 2u * PHILOX_W1);
+  c.c3 = l0;
+  return c;
+}
+
+__device__ __forceinline__ LaneShared lane_shared(uint32_t sseed, uint32_t k) {
+  uint32_t h0, l0, h1, l1;
+  mulwide(k ^ sseed, PHILOX_M0, h0, l0);                              // round 1, p0
+  mulwide(h0 ^ (STREAM_KEY1 + PHILOX_W1), PHILOX_M1, h1, l1);         // round 2, p1
+  LaneShared s;
+  s.h = h1; s.l = l1; s.l0 = l0;
+  return s;
+}
+
+// rounds 3..9 from the factored state
+__device__ __forceinline__ void stream_block_tail(uint32_t sseed, const LaneShared& ls, const QuadConst& qc, uint32_t (&o)[4]) {
+  uint32_t c0 = ls.h ^ qc.a, c1 = ls.l, c2 = ls.l0 ^ qc.b, c3 = qc.c3;
+#pragma unroll
+  for (int r = 3; r < 10; ++r) {
+    uint32_t h0, l0, h1, l1;
+    mulwide(c0, PHILOX_M0, h0, l0);
+    mulwide(c2, PHILOX_M1, h1, l1);
+    uint32_t n0 = h1 ^ c1 ^ (sseed + (uint32_t)r * PHILOX_W0);
+    uint32_t n2 = h0 ^ c3 ^ (STREAM_KEY1 + (uint32_t)r * PHILOX_W1);
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
 // Two N(0,1) values from two Philox words (Box-Muller, 23-bit uniforms).
@@ -54,6 +110,13 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, 
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
   ze = __fmul_rn(r, c);
   zo = __fmul_rn(r, s);
+}
+
+__device__ __forceinline__ void normal_quad_tail(uint32_t sseed, const LaneShared& ls, const QuadConst& qc, float (&z)[4]) {
+  uint32_t o[4];
+  stream_block_tail(sseed, ls, qc, o);
+  box_muller(o[0], o[1], z[0], z[1]);
+  box_muller(o[2], o[3], z[2], z[3]);
 }
 
 __device__ __forceinline__ void normal_quad(uint32_t sseed, uint32_t k, uint32_t q, float (&z)[4]) {

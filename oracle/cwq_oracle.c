@@ -59,7 +59,7 @@ void cwqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 }
 
 /* ---- the normal stream z(stream_seed, k, d): spec section 3.2 ----
- * block(k, q) = philox(ctr = (k, q, 0, 0), key = (stream_seed, 42)); lanes (0,1) -> dims 4q, 4q+1;
+ * block(k, q) = philox(ctr = (0, k, 0, q), key = (stream_seed, 42)); lanes (0,1) -> dims 4q, 4q+1;
  * lanes (2,3) -> dims 4q+2, 4q+3.  The oracle evaluates the float transform with libm; the engine
  * uses MUFU approximations, so engine draws are injected when bit-exact indices are asserted. */
 static inline void box_muller(uint32_t xa, uint32_t xb, float* ze, float* zo) {
@@ -74,7 +74,7 @@ static inline void box_muller(uint32_t xa, uint32_t xb, float* ze, float* zo) {
 }
 
 static inline void normal_quad(uint32_t sseed, uint32_t k, uint32_t q, float z[4]) {
-  uint32_t ctr[4] = {k, q, 0u, 0u}, key[2] = {sseed, STREAM_KEY1}, o[4];
+  uint32_t ctr[4] = {0u, k, 0u, q}, key[2] = {sseed, STREAM_KEY1}, o[4];
   cwqo_philox4x32_10(ctr, key, o);
   box_muller(o[0], o[1], &z[0], &z[1]);
   box_muller(o[2], o[3], &z[2], &z[3]);
@@ -94,7 +94,7 @@ void cwqo_normals(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, float* o
 void cwqo_stream_words(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out) {
   for (uint32_t i = 0; i < nk; ++i)
     for (uint32_t q = 0; q < nq; ++q) {
-      uint32_t ctr[4] = {k0 + i, q, 0u, 0u}, key[2] = {sseed, STREAM_KEY1};
+      uint32_t ctr[4] = {0u, k0 + i, 0u, q}, key[2] = {sseed, STREAM_KEY1};
       cwqo_philox4x32_10(ctr, key, out + ((size_t)i * nq + q) * 4);
     }
 }

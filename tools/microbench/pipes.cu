@@ -10,7 +10,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
   fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
-constexpr int ITERS = 4096;
+constexpr int ITERS = 16384;
 constexpr int U = 8;  // independent chains per thread
 
 template <int OP>
@@ -48,6 +48,13 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, uint32_t seed, long
       if (OP == 12) { unsigned long long w = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (uint32_t)(w >> 32) ^ (uint32_t)w; f[i] = __fmaf_rn(f[i], c1, c2); } // IMAD.WIDE + LOP + FFMA
       if (OP == 13) { f[i] = __cosf(f[i]) + 1.5f; }
       if (OP == 14) { u[i] = __float_as_uint((float)u[i]) + 3u; }                // I2F
+      if (OP == 15) { unsigned long long w; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(u[i]), "r"(0xD2511F53u), "l"(((unsigned long long)v[i] << 32) | u[i])); u[i] = (uint32_t)w; v[i] = (uint32_t)(w >> 32); }  // pure IMAD.WIDE chain
+      if (OP == 16) { double d = __hiloint2double((int)v[i], (int)u[i]); d = __fma_rn(d, 1.0000001, 1e-9); u[i] = (uint32_t)__double2loint(d); v[i] = (uint32_t)__double2hiint(d) & 0x3fffffffu | 0x30000000u; }  // DFMA chain
+      if (OP == 17) { // hi32(u*M) via one DFMA.RZ: fma.rz(2^52+u, M*2^-32, 2^52 - M*2^20); lo via IMAD
+        double a = __hiloint2double(0x43300000, (int)u[i]);
+        double h = __fma_rz(a, 3528531795.0 * 2.3283064365386963e-10, 4503599627370496.0 - 3528531795.0 * 1048576.0);
+        u[i] = (uint32_t)__double2loint(h) ^ (u[i] * 0xD2511F53u);
+      }
     }
   }
   long long t1 = clock64();
@@ -176,6 +183,9 @@ int main() {
     run_pipe<8>("MUFU.RSQ(+FADD)", 1, sms, d_out, d_cyc, bps, 256);
     run_pipe<9>("MUFU.EX2(+FMUL)", 1, sms, d_out, d_cyc, bps, 256);
     run_pipe<14>("I2F(+IADD)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<15>("IMAD.WIDE pure (mad.wide)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<16>("DFMA(+2 LOP)", 1, sms, d_out, d_cyc, bps, 256);
+    run_pipe<17>("hi via DFMA.RZ + IMAD lo + LOP", 1, sms, d_out, d_cyc, bps, 256);
     run_pipe<11>("FFMA+LOP3 pair", 1, sms, d_out, d_cyc, bps, 256);
     run_pipe<12>("IMAD.WIDE+LOP+FFMA triple", 1, sms, d_out, d_cyc, bps, 256);
     run_comp<0>("philox only (per 4 u32 = 4cd)", sms, d_out, d_cyc, d_coef, bps);
