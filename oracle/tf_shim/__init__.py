@@ -25,6 +25,7 @@ import types
 import numpy as np
 
 _state = {"normal_source": None, "outlier_seed": 0}
+_ctx = []   # stack of (feed, memo) of the Session.run calls in flight: loop bodies close over placeholders
 
 
 def set_normal_source(fn):
@@ -57,10 +58,13 @@ _NP2DT = {np.dtype(np.float32): float32, np.dtype(np.float64): float64, np.dtype
 
 
 class TensorShape:
-    def __init__(self, dims):
-        self.dims = dims
+    def __init__(self, dims, tensor=None):
+        self.dims, self.tensor = dims, tensor
 
     def as_list(self):
+        if self.tensor is not None:
+            # static shape inference is not modelled: evaluate (works whenever no placeholder is involved)
+            return list(np.shape(self.tensor.eval({}, {})))
         return list(self.dims)
 
 
@@ -74,12 +78,12 @@ class Tensor:
     def eval(self, feed, memo):
         key = id(self)
         if key in memo:
-            return memo[key]
+            return memo[key][1]
         if key in feed:
             v = feed[key]
         else:
             v = self.fn(*[_ev(i, feed, memo) for i in self.inputs])
-        memo[key] = v
+        memo[key] = (self, v)   # the node is kept alive so a recycled id() can never alias a stale entry
         return v
 
     @property
@@ -88,7 +92,9 @@ class Tensor:
 
     @property
     def shape(self):
-        return TensorShape(self._static_shape if self._static_shape is not None else [None])
+        if self._static_shape is not None:
+            return TensorShape(self._static_shape)
+        return TensorShape([None], tensor=self)
 
     def get_shape(self):
         return self.shape
@@ -108,6 +114,7 @@ class Tensor:
     def __ge__(self, o): return _binary(np.greater_equal, self, o, keep=False)
     def __gt__(self, o): return _binary(np.greater, self, o, keep=False)
     __hash__ = object.__hash__
+    __array_ufunc__ = None   # numpy arrays defer to the reflected operators above (ndarray * Tensor -> Tensor)
 
     def __getitem__(self, item):
         items = item if isinstance(item, tuple) else (item,)
@@ -294,6 +301,8 @@ def numpy_function(func, inp, Tout):
         for a in args:
             if isinstance(a, (list, tuple)):
                 a = np.array(list(a), dtype=object)
+            elif isinstance(a, np.ndarray):
+                a = a.copy()   # py functions get their own buffers (binary_io.to_bit_string divides its argument in place)
             conv.append(a)
         r = func(*conv)
         if isinstance(Tout, (list, tuple)):
@@ -307,11 +316,16 @@ def numpy_function(func, inp, Tout):
     return node
 
 
+def _sub_eval(node):
+    feed, memo = _ctx[-1] if _ctx else ({}, {})
+    return _ev(node, feed, memo)
+
+
 def map_fn(fn, elems, dtype=None):
     def run(e):
         out = []
         for x in np.asarray(e):
-            out.append(_ev(fn(convert(x)), {}, {}))
+            out.append(_sub_eval(fn(convert(x))))
         return np.array(out, dtype=object)
     return Tensor(run, [elems], dtype)
 
@@ -323,10 +337,10 @@ def while_loop(cond, body, loop_vars, shape_invariants=None):
         cur = list(vals)
         while True:
             nodes = [convert(v) for v in cur]
-            if not bool(_ev(cond(*nodes), {}, {})):
+            if not bool(_sub_eval(cond(*nodes))):
                 break
             res = body(*nodes)
-            cur = [_ev(r, {}, {}) for r in res]
+            cur = [_sub_eval(r) for r in res]
         return tuple(cur)
     node = Tensor(run, list(loop_vars))
     return [Tensor(lambda r, j=j: r[j], [node], getattr(loop_vars[j], "_dtype", None)) for j in range(n)]
@@ -355,7 +369,11 @@ class Session:
     def run(self, fetches, feed_dict=None):
         feed = {id(k): (np.asarray(v) if not isinstance(v, (bytes, str)) else v) for k, v in (feed_dict or {}).items()}
         memo = {}
-        return _ev(fetches, feed, memo)
+        _ctx.append((feed, memo))
+        try:
+            return _ev(fetches, feed, memo)
+        finally:
+            _ctx.pop()
 
 
 # ----------------------------------------------------------------------------------------------

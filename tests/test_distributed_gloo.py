@@ -1,0 +1,113 @@
+"""Host-side sharding logic on CPU with the gloo backend, world_size 2: balanced contiguous ranges,
+ragged all-gather, and the importance-sampler shard driver run on a stand-in job whose encode stage is
+the CPU oracle (the GPU stage is covered by the -m gpu tests)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Groups:
+    pass
+
+
+class FakeISJob:
+    """Same attributes distributed.make_is_shard touches; encode() is the oracle on the given range."""
+
+    def __init__(self, a, b, starts, K, seed):
+        from oracle import oracle as O
+        self.O, self.a, self.b, self.seed = O, a, b, seed
+        self.groups = _Groups()
+        self.groups.starts = torch.from_numpy(starts)
+        self.K = torch.from_numpy(K)
+        self.index = torch.zeros(len(K), dtype=torch.int32)
+        self.encoded = None
+
+    def encode(self, g0, g1):
+        idx, _ = self.O.is_encode_groups(self.a, self.b, self.groups.starts.numpy(), self.K.numpy(), self.seed, g0, g1, 1)
+        self.index[g0:g1] = torch.from_numpy(idx[g0:g1].view(np.int32))
+        self.encoded = (g0, g1)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from compression_without_quantization_b200 import distributed as D
+    from oracle import oracle as O
+    try:
+        # ragged all-gather
+        bounds = [0, 5, 12] if world == 2 else [0, 12]
+        local = torch.arange(bounds[rank], bounds[rank + 1], dtype=torch.int32) * 3
+        full = D.all_gather_ranges(local, bounds)
+        assert full.tolist() == [3 * i for i in range(12)]
+        local2 = torch.arange(bounds[rank], bounds[rank + 1], dtype=torch.int32)[:, None].repeat(1, 4)
+        assert D.all_gather_ranges(local2, bounds)[:, 2].tolist() == list(range(12))
+        # sharded importance sampler on a small problem
+        rng = np.random.default_rng(5)
+        n = 600
+        q_loc = (rng.normal(size=n) * (rng.random(n) < .4)).astype(np.float32)
+        q_scale = np.exp(-np.abs(rng.normal(0, .7, n))).astype(np.float32)
+        t_loc, t_scale, kl, mask = O.is_prologue(q_loc, q_scale, np.zeros(n, np.float32), np.ones(n, np.float32), 8)
+        starts = O.group(kl, 10, 3, True)
+        total, K = O.group_totals(kl, starts)
+        a, b = O.is_coef(t_loc, t_scale)
+        job = FakeISJob(a, b, starts, K, 42)
+        D.make_is_shard()(job)
+        want, _ = O.is_encode_groups(a, b, starts, K, 42)
+        assert np.array_equal(job.index.numpy().view(np.uint32), want)
+        g0, g1 = job.encoded
+        assert (g0, g1) == (job.shard_bounds[rank], job.shard_bounds[rank + 1]) and 0 < g1 - g0 < len(K)
+        work = D.is_work(job).numpy().astype(np.float64)
+        shares = [work[job.shard_bounds[r]:job.shard_bounds[r + 1]].sum() / work.sum() for r in range(world)]
+        assert max(shares) < 0.5 + work.max() / work.sum() + 1e-9
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_ranges_single_process():
+    from compression_without_quantization_b200 import distributed as D
+    w = np.array([5, 1, 1, 1, 1, 1, 5, 5, 1, 9], dtype=np.int64)
+    for world in (1, 2, 3, 4, 8):
+        b = D.balanced_ranges(w, world)
+        assert b[0] == 0 and b[-1] == len(w) and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+    b = D.balanced_ranges(w, 2)
+    assert abs(w[:b[1]].sum() - w.sum() / 2) <= w.max()
+    assert D.balanced_ranges(np.zeros(0), 4) == [0, 0, 0, 0, 0]
+    big = np.random.default_rng(0).integers(1, 400000, 100000)
+    b8 = D.balanced_ranges(big, 8)
+    parts = [big[b8[r]:b8[r + 1]].sum() for r in range(8)]
+    assert max(parts) / (big.sum() / 8) < 1.01   # imbalance well under the 12 % that 7x on 8 GPUs tolerates
+
+
+@pytest.mark.timeout(120)
+def test_sharded_encode_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

@@ -1,0 +1,164 @@
+"""CPU tests of the oracle (test infrastructure): Philox known answers, the reference's own bit helpers,
+the grouping examples verified in SURVEY.md appendix A, and the goldens produced by running the
+UNMODIFIED reference sampler sources under oracle/tf_shim (tests/golden/gen_reference_goldens.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def test_philox4x32_10_known_answers(oracle):
+    # Random123 kat_vectors (philox4x32 10), also SURVEY.md appendix A
+    kats = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+            ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kats:
+        assert list(oracle.philox4x32_10(ctr, key)) == want
+
+
+def test_stream_is_philox_on_counter_0_k_0_q(oracle):
+    w = oracle.stream_words(42, 7, 3, 2)
+    for i in range(3):
+        for q in range(2):
+            assert list(w[i, q]) == list(oracle.philox4x32_10([0, 7 + i, 0, q], [42, 42]))
+
+
+def test_normal_stream_statistics_and_addressing(oracle):
+    z = oracle.default_normal_source(42, 0, 40000, 16)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3 and abs(np.mean(z ** 4) - 3) < 0.05
+    assert np.abs(z).max() < 5.7   # 23-bit uniforms: r <= sqrt(-2 ln 2^-23)
+    assert np.array_equal(oracle.default_normal_source(42, 100, 5, 7), z[100:105, :7])
+    assert not np.array_equal(oracle.default_normal_source(43, 0, 4, 16), z[:4])
+
+
+def test_deterministic_log_exp_accuracy(oracle):
+    rng = np.random.default_rng(0)
+    xs = np.exp(rng.uniform(-30, 30, 4000)).astype(np.float32)
+    got = np.array([oracle.detlogf(float(x)) for x in xs])
+    assert np.max(np.abs(got - np.log(xs.astype(np.float64))) / np.maximum(np.abs(np.log(xs.astype(np.float64))), 1e-2)) < 3e-7
+    xe = rng.uniform(-10, 21.4, 4000).astype(np.float32)
+    ge = np.array([oracle.detexpf(float(x)) for x in xe])
+    assert np.max(np.abs(ge / np.exp(xe.astype(np.float64)) - 1)) < 3e-7
+    assert oracle.detexpf(0.0) == 1.0 and oracle.detlogf(1.0) == 0.0
+
+
+def test_binary_io_against_reference_module_goldens(oracle):
+    g = json.load(open(os.path.join(GOLD, "binary_io.json")))
+    for x, code in g["elias_delta"]:
+        assert oracle.elias_delta_code(x) == code
+        assert oracle.elias_delta_decode((code + "0110").encode()) == (x, len(code))
+    for v, bits, s in g["to_bit_string"]:
+        assert oracle.to_bit_string(v, bits) == s and oracle.from_bit_string(s) == v
+    with pytest.raises(Exception, match="bigger than what we can encode"):
+        oracle.to_bit_string(8, 3)
+
+
+def test_grouping_examples_from_survey(oracle):
+    kl = np.full(40, 1e-6, np.float32)
+    assert list(oracle.group(kl, 20, 2, True)) == list(range(0, 40, 4)) + [39, 40]
+    assert list(oracle.group(kl, 20, 4, True)) == [0, 16, 32, 39, 40]
+    assert list(oracle.group(kl, 20, 3, False)) == [0, 7, 14, 21, 28, 35, 39, 40]
+    assert list(oracle.group(np.array([100, 1e-3, 1e-3, 1e-3], np.float32), 20, 4, True)) == [0, 0, 1, 3, 4]
+    assert list(oracle.group(np.array([0.1], np.float32), 20, 4, True)) == [0, 0, 1]
+    assert oracle.size_limit(4, True) == 16 and oracle.size_limit(12, False) == 4095 and oracle.size_limit(2, True) == 4
+
+
+def test_grouping_matches_verbatim_python_loop(oracle):
+    """CIS:178-204 / CGS:223-252 transcribed literally (numpy float32 accumulator, float64 budget)."""
+    rng = np.random.default_rng(3)
+    for strict, m, bits in [(True, 4, 20), (True, 2, 8), (False, 5, 30), (False, 12, 420)]:
+        kl_divs = (rng.gamma(0.6, 0.9, 3000)).astype(np.float32)
+        starts = [0]
+        size, acc = 0, 0
+        budget = bits * np.log(2) - 1
+        n = kl_divs.size
+        for idx in range(n):
+            gb = np.log(size + 1) / np.log(2)
+            hit = (gb > m or acc + kl_divs[idx] > budget) if strict else (gb >= m or acc + kl_divs[idx] >= budget)
+            if hit or idx == n - 1:
+                starts.append(idx)
+                size, acc = 1, kl_divs[idx]
+            else:
+                acc += kl_divs[idx]
+                size += 1
+        starts += [n]
+        assert list(oracle.group(kl_divs, bits, m, strict)) == starts
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "reference_samplers.npz"))
+
+
+@pytest.mark.parametrize("name", ["is0", "is1", "is2", "is3", "is4"])
+def test_importance_sampler_matches_unmodified_reference_run(oracle, gold, name):
+    q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
+    seed, bits, m, limit = [int(x) for x in gold[name + "_par"]]
+    s, code, starts, (oi, oq) = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale),
+                                                                      oracle.Normal(p_loc, p_scale), seed, bits, m, limit)
+    assert np.array_equal(starts, gold[name + "_starts"])
+    assert code == gold[name + "_bitcode"].tobytes()
+    assert np.array_equal(oi, gold[name + "_oidx"]) and np.array_equal(oq, gold[name + "_oq"])
+    assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6)
+    st2, kls = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), seed,
+                                                     bits, m, limit, return_group_indices_only=True)
+    assert np.allclose(kls, gold[name + "_group_kls"], rtol=2e-5, atol=1e-6)   # TFP KL formula vs spec kl01: same value
+    if gold[name + "_decoded"].size:
+        lst = [int(x) for x in starts[:-1]]
+        d = oracle.decode_grouped_importance_sample(None, code, lst, oracle.Normal(p_loc, p_scale), bits, seed, oi, oq)
+        assert lst[-1] == q_loc.size
+        assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
+
+
+def test_is4_covers_outliers_and_empty_first_group(gold):
+    assert list(gold["is4_oidx"]) == [10, 33, 43] and list(gold["is4_starts"][:3]) == [0, 0, 1]
+
+
+@pytest.mark.parametrize("name", ["gr0", "gr1", "gr2"])
+def test_greedy_sampler_matches_unmodified_reference_run(oracle, gold, name):
+    q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
+    seed, steps, b, m = [int(x) for x in gold[name + "_par"]]
+    s, code, starts = oracle.code_grouped_greedy_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), steps,
+                                                        b, seed, m)
+    assert starts == [int(x) for x in gold[name + "_starts"]]
+    assert code.encode() == gold[name + "_bitcode"].tobytes()
+    assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6)
+    d = oracle.decode_grouped_greedy_sample(None, code, starts[:-1], oracle.Normal(p_loc, p_scale), b, steps, seed)
+    assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(d, s)
+
+
+def test_oracle_round_trips_and_injection_seam(oracle):
+    rng = np.random.default_rng(1)
+    n = 500
+    q_loc = (rng.normal(size=n) * (rng.random(n) < .4)).astype(np.float32)
+    q_scale = np.exp(-np.abs(rng.normal(0, .7, n))).astype(np.float32)
+    p = oracle.Normal(np.zeros(n, np.float32), np.ones(n, np.float32))
+    s, code, starts, (oi, oq) = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), p, 42, 10, 3, 6)
+    d = oracle.decode_grouped_importance_sample(None, code, [int(x) for x in starts[:-1]], p, 10, 42, oi, oq)
+    inl = np.ones(n, bool)
+    inl[oi] = False
+    assert np.array_equal(d[inl], s[inl]) and np.all(np.abs(d[oi] - s[oi]) <= 60 / 65535 + 1e-6)
+    # an injected source that returns the default stream must change nothing; a different one must
+    calls = []
+
+    def src(seed, k0, nk, G):
+        calls.append((seed, k0, nk, G))
+        return oracle.default_normal_source(seed, k0, nk, G)
+    s2, code2, _, _ = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), p, 42, 10, 3, 6, normal_source=src)
+    assert code2 == code and np.array_equal(s2, s) and calls[0][0] in (42, (42 + 0x9E3779B9) & 0xFFFFFFFF)
+    s3, code3, _, _ = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), p, 42, 10, 3, 6,
+                                                            normal_source=lambda sd, k0, nk, G: oracle.default_normal_source(sd + 1, k0, nk, G))
+    assert code3 != code
+
+
+def test_quantizer_round_trip(oracle):
+    x = np.array([-40, -30, -1.234, 0.0, 5.5, 29.9999, 30, 99], np.float32)
+    q = oracle.quantize_u16(x)
+    assert q[0] == 0 and q[1] == 0 and q[-1] == 65535 and q[-2] == 65535
+    assert np.all(np.abs(oracle.dequantize_u16(q)[1:-1] - np.clip(x, -30, 30)[1:-1]) <= 30 / 65535 + 1e-6)
