@@ -4,8 +4,8 @@
 // associative, so a prefix sum would move boundaries.  Here it is evaluated EXACTLY but in parallel:
 //   1. k_next:       next[i] = where the following boundary falls if a group starts at dim i
 //                    (a bounded sequential fp32 walk per dim, all dims in parallel);
-//   2. k_tile_exit:  pointer jumping inside 1024-dim tiles -> exit1[i] = first chain node past the tile;
-//   3. k_super_exit: the same over 64-tile super-tiles, only for the few possible entry nodes;
+//   2. k_tile_exit:  pointer jumping inside 4096-dim tiles -> exit1[i] = first chain node past the tile;
+//   3. k_super_exit: the same over 32-tile super-tiles, only for the few possible entry nodes;
 //   4. k_chain_top / k_tile_entries / k_mark: follow the one true chain 0 -> ... -> n top-down;
 //   5. a device scan compacts the marked boundaries into starts[], gid[], per-segment offsets.
 #include "cwq_common.cuh"
@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) k_is_prologue(const float* __restrict__ q
                                                      uint8_t* __restrict__ mask) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float limit = segs[find_segment(segs, n_seg, i)].dim_kl_bit_limit;
+  const cwq_segment& sg = segs[find_segment(segs, n_seg, i)];
+  float limit = sg.dim_kl_bit_limit;
   float ps = p_scale[i];
   float tl = __fdiv_rn(__fsub_rn(q_loc[i], p_loc[i]), ps);
   float ts = __fdiv_rn(q_scale[i], ps);
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) k_is_prologue(const float* __restrict__ q
   uint8_t m = 0;
   if (!(kl_bits <= limit)) { m |= 1; tl = 0.0f; ts = 1.0f; }
   if (kl_bits > limit) m |= 2;
+  if (i == sg.start) m |= 4;   // first dim of a segment (outlier compaction reads its per-segment offsets here)
   kl[i] = kl01(tl, ts);
   float iv = __fdiv_rn(1.0f, __fmul_rn(ts, ts));
   coef[i] = make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
@@ -52,8 +54,8 @@ __global__ void __launch_bounds__(256) k_greedy_prologue(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // grouping
 // ------------------------------------------------------------------------------------------
-constexpr int TILE1 = 1024;          // nodes per tile
-constexpr int TILES_PER_SUPER = 64;  // tiles per super-tile
+constexpr int TILE1 = 4096;          // nodes per tile (its next[] slice lives in shared memory: 16 KB)
+constexpr int TILES_PER_SUPER = 32;  // tiles per super-tile
 constexpr long long TILE2 = (long long)TILE1 * TILES_PER_SUPER;
 
 // the reference's loop body from state (size, acc) at dim idx0, until the next boundary
@@ -155,16 +157,25 @@ __global__ void __launch_bounds__(128) k_tile_entries(const int* __restrict__ en
   }
 }
 
-__global__ void __launch_bounds__(128) k_mark(const int* __restrict__ entry1, const int* __restrict__ next, long long n,
+// one CTA per tile: the tile's next[] slice is staged in shared memory (coalesced), then one thread
+// follows the chain through it (dependent shared loads instead of dependent global loads)
+__global__ void __launch_bounds__(256) k_mark(const int* __restrict__ entry1, const int* __restrict__ next, long long n,
                                               long long n_tiles, uint8_t* __restrict__ mark) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int snext[TILE1];
+  const long long t = blockIdx.x;
   if (t >= n_tiles) return;
-  long long v = entry1[t];
-  if (v < 0) return;
-  long long t_end = (t + 1) * TILE1 < n ? (t + 1) * TILE1 : n;
-  while (v < t_end) {
-    mark[v] |= 1;
-    v = next[v];
+  const long long v0 = entry1[t];
+  if (v0 < 0) return;
+  const long long tile0 = t * TILE1;
+  const long long t_end = tile0 + TILE1 < n ? tile0 + TILE1 : n;
+  for (int j = threadIdx.x; j < TILE1; j += blockDim.x) snext[j] = (tile0 + j < n) ? next[tile0 + j] : (int)n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long v = v0;
+    while (v < t_end) {
+      mark[v] |= 1;
+      v = snext[v - tile0];
+    }
   }
 }
 
@@ -333,7 +344,7 @@ extern "C" int cwq_group(const float* kl, int64_t n, const cwq_segment* segments
   CWQ_LAUNCH_CHECK();
   k_tile_entries<<<(unsigned)((n_super + 127) / 128), 128, 0, st>>>(entry2, exit1, n, n_super, entry1);
   CWQ_LAUNCH_CHECK();
-  k_mark<<<(unsigned)((n_tiles + 127) / 128), 128, 0, st>>>(entry1, next, n, n_tiles, mark);
+  k_mark<<<(unsigned)n_tiles, 256, 0, st>>>(entry1, next, n, n_tiles, mark);
   CWQ_LAUNCH_CHECK();
   k_mark_segment_starts<<<(n_segments + 127) / 128, 128, 0, st>>>(segments, n_segments, mark);
   CWQ_LAUNCH_CHECK();

@@ -199,8 +199,11 @@ struct OutlierDeliver {
   uint16_t* outlier_q;
   long long* seg_outlier_off;
   __device__ void operator()(long long i, uint32_t pre, uint32_t cnt) const {
-    if (cnt == 0) return;
+    const uint8_t m = mask[i];
+    if ((m & 6) == 0) return;
     int s = find_segment(segs, n_seg, i);
+    if (m & 4) seg_outlier_off[s] = (long long)pre;   // outliers before this segment
+    if (cnt == 0) return;
     long long local = i - segs[s].start;
     float z[4];
     normal_quad(segs[s].seed + OUTLIER_STREAM_OFFSET, (uint32_t)local, 0u, z);
@@ -210,22 +213,8 @@ struct OutlierDeliver {
     outlier_q[pre] = quantize_u16(v);
   }
 };
-// seg_outlier_off[s] = number of outliers before segment s: counted per segment by one warp each
-__global__ void __launch_bounds__(256) k_seg_outlier_count(const uint8_t* __restrict__ mask, const cwq_segment* __restrict__ segs,
-                                                           int n_seg, unsigned int* __restrict__ counts) {
-  int s = blockIdx.x;
-  if (s >= n_seg) return;
-  unsigned int c = 0;
-  for (long long i = segs[s].start + threadIdx.x; i < segs[s].end; i += blockDim.x) c += (mask[i] >> 1) & 1;
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[s], c);
-}
-__global__ void k_seg_outlier_offsets(const unsigned int* __restrict__ counts, int n_seg, long long* __restrict__ off) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    long long a = 0;
-    for (int s = 0; s < n_seg; ++s) { off[s] = a; a += counts[s]; }
-    off[n_seg] = a;
-  }
+__global__ void k_outlier_finish(const uint32_t* __restrict__ total, int n_seg, long long* __restrict__ off) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) off[n_seg] = (long long)*total;
 }
 
 __global__ void __launch_bounds__(256) k_outlier_decode(float* __restrict__ sample, const long long* __restrict__ pos,
@@ -569,7 +558,7 @@ extern "C" int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, 
 
 extern "C" size_t cwq_outlier_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  return align_up((size_t)scan_tiles(n) * 4) + 4096 + (1 << 22);  // tile sums + per-segment counters (<= 2^20 segments)
+  return align_up((size_t)scan_tiles(n) * 4) + 4096;  // tile sums + scalars
 }
 
 extern "C" int cwq_outlier_encode(const float* q_loc, const float* q_scale, const uint8_t* mask, int64_t n,
@@ -580,17 +569,14 @@ extern "C" int cwq_outlier_encode(const float* q_loc, const float* q_scale, cons
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws(workspace, workspace_bytes);
   uint32_t* tile_sums = ws.take<uint32_t>((size_t)scan_tiles(n));
-  unsigned int* counts = ws.take<unsigned int>((size_t)n_segments);
-  if (!tile_sums || !counts) { set_error("cwq_outlier_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
-  CWQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * (size_t)n_segments, st));
-  k_seg_outlier_count<<<n_segments, 256, 0, st>>>(mask, segments, n_segments, counts);
-  CWQ_LAUNCH_CHECK();
-  k_seg_outlier_offsets<<<1, 32, 0, st>>>(counts, n_segments, (long long*)seg_outlier_off);
-  CWQ_LAUNCH_CHECK();
+  uint32_t* total = ws.take<uint32_t>(1);
+  if (!tile_sums || !total) { set_error("cwq_outlier_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
   OutlierCount in{mask};
   OutlierDeliver out{mask, q_loc, q_scale, segments, n_segments, sample, (long long*)outlier_idx, outlier_q,
                      (long long*)seg_outlier_off};
-  CWQ_CUDA((device_exclusive_scan<uint32_t, OutlierCount, OutlierDeliver>(in, out, n, tile_sums, nullptr, st)));
+  CWQ_CUDA((device_exclusive_scan<uint32_t, OutlierCount, OutlierDeliver>(in, out, n, tile_sums, total, st)));
+  k_outlier_finish<<<1, 32, 0, st>>>(total, n_segments, (long long*)seg_outlier_off);
+  CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }
 

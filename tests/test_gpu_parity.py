@@ -70,6 +70,7 @@ def test_draws_match_libm_box_muller(cwq, oracle):
 @pytest.mark.parametrize("n,bits,m,limit,nontrivial", [
     (20000, 20, 4, 16, False), (20000, 8, 4, 6, False), (20000, 12, 2, 10, True), (5000, 16, 4, 14, True),
     (1, 20, 4, 16, False), (2, 20, 4, 16, False), (1025, 20, 0, 16, False), (70000, 20, 4, 16, False),
+    (400003, 20, 4, 16, False), (4097, 20, 4, 16, True), (131072, 12, 3, 10, False),
 ])
 def test_is_grouping_bit_exact(cwq, oracle, syn, n, bits, m, limit, nontrivial):
     q_loc, q_scale, p_loc, p_scale = syn.synthetic_posterior(n, 3, nontrivial)
@@ -79,6 +80,24 @@ def test_is_grouping_bit_exact(cwq, oracle, syn, n, bits, m, limit, nontrivial):
                                                             42, bits, m, limit, return_group_indices_only=True)
     assert np.array_equal(starts, o_starts)
     assert np.array_equal(np.asarray(kls, dtype=np.float64), np.asarray(o_kls, dtype=np.float64))
+
+
+@pytest.mark.parametrize("n,steps,bits,m", [(300001, 30, 14, 12), (50000, 4, 6, 5), (4096, 2, 3, 0), (140000, 30, 14, 16)])
+def test_greedy_grouping_bit_exact_at_scale(cwq, oracle, syn, n, steps, bits, m):
+    """Grouping only (no candidate loop): tile / super-tile boundaries, 4095-dim and larger groups."""
+    import torch
+    from compression_without_quantization_b200 import engine as E
+    q_loc, q_scale, p_loc, p_scale = syn.synthetic_posterior(n, 6, True)
+    dev = E.cuda_device()
+    job = E.GreedyJob(*(torch.from_numpy(x).to(dev) for x in (q_loc, q_scale, p_loc, p_scale)),
+                      [E.SegmentSpec(n, 42, steps * bits, m, float("inf"), False)], steps, bits).prepare()
+    t_loc, t_scale, kl = oracle.greedy_prologue(q_loc, q_scale, p_loc, p_scale)
+    starts = oracle.group(kl, steps * bits, m, False)
+    assert np.array_equal(job.groups.starts.cpu().numpy(), starts)
+    assert np.array_equal(job.kl.cpu().numpy().view(np.uint32), kl.view(np.uint32))
+    gid = job.groups.gid.cpu().numpy()
+    assert np.array_equal(gid, np.searchsorted(starts[1:], np.arange(n), side="right"))
+    assert np.array_equal(job.groups.group_seed.cpu().numpy().view(np.uint32), (42 + np.arange(len(starts) - 1)).astype(np.uint32))
 
 
 def test_first_dim_over_budget_gives_empty_group(cwq, oracle, syn):

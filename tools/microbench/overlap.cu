@@ -74,5 +74,11 @@ int main() {
   run<4, 2, 6, 0>("W+M+L", sms, d_out);
   run<4, 2, 6, 5>("W+M+L+F", sms, d_out);
   run<8, 4, 12, 10>("2x(W+M+L+F)", sms, d_out);
+  // the score kernel's own mix per 5 candidate-dims: 18 IMAD.WIDE, 10 MUFU, ~28 ALU (9 L = 27), 25 FP32
+  run<18, 10, 9, 25>("kernel mix / 5 cd", sms, d_out);
+  run<18, 10, 0, 25>("kernel mix / 5 cd, no ALU", sms, d_out);
+  run<18, 0, 0, 25>("kernel mix / 5 cd, W+F", sms, d_out);
+  run<18, 10, 0, 0>("kernel mix / 5 cd, W+M", sms, d_out);
+  run<9, 5, 4, 12>("kernel mix / 2.5 cd", sms, d_out);
   return 0;
 }
