@@ -121,32 +121,35 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
 def _segment_result(job, s, host, return_indices):
     g0, g1 = job.segment_group_range(s)
     a, b = job.table.starts[s], job.table.starts[s] + job.table.specs[s].n
-    sample = host["sample"][a:b].copy()
+    sample = host["sample"][a:b]
     starts = host["starts"][g0:g1 + 1] - a
     o0, o1 = int(host["seg_outlier_off"][s]), int(host["seg_outlier_off"][s + 1])
-    outlier_extras = (host["outlier_idx"][o0:o1].copy(), host["outlier_q"][o0:o1].copy())
+    outlier_extras = (host["outlier_idx"][o0:o1], host["outlier_q"][o0:o1])
     if return_indices:
         indices = [np.int64(i) + 1 for i in host["index"][g0:g1]]
         return sample, indices, starts, outlier_extras
     bit0, bit1 = int(host["bit_off"][g0]), int(host["bit_off"][g1])
-    bitcode = E.bits_to_ascii(host["bits"], bit1 - bit0, bit0)
+    bitcode = host["ascii"][bit0:bit1].tobytes()
     return sample, bitcode, starts, outlier_extras
 
 
 def _host_views(job, with_bits):
-    n_out = int(job.seg_outlier_off[-1].item())
-    host = {
-        "sample": job.sample.cpu().numpy(),
-        "starts": job.groups.starts.cpu().numpy(),
-        "index": job.index.cpu().numpy().view(np.uint32),
-        "seg_outlier_off": job.seg_outlier_off.cpu().numpy(),
-        "outlier_idx": job.outlier_idx[:n_out].cpu().numpy(),
-        "outlier_q": _u16_view(job.outlier_q[:n_out]),
-    }
+    """One batch of device->host copies for everything the caller gets back."""
+    off = job.seg_outlier_off.cpu().numpy()
+    n_out = int(off[-1])
+    names = ["sample", "starts", "index", "outlier_idx", "outlier_q"]
+    tensors = [job.sample, job.groups.starts, job.index, job.outlier_idx[:n_out], job.outlier_q[:n_out]]
     if with_bits:
-        host["bit_off"] = job.bit_off.cpu().numpy()
-        total_bytes = (int(host["bit_off"][-1]) + 7) // 8
-        host["bits"] = job.bits[:total_bytes].cpu().numpy()
+        names += ["bit_off", "bits"]
+        tensors += [job.bit_off, job.bits]
+    host = dict(zip(names, E.to_host(tensors)))
+    host["seg_outlier_off"] = off
+    host["index"] = host["index"].view(np.uint32)
+    host["outlier_q"] = host["outlier_q"].view(np.uint16)
+    if with_bits:
+        total_bits = int(host["bit_off"][-1])
+        # packed MSB-first bits -> the reference's '0'/'1' characters, once for the whole batch
+        host["ascii"] = np.unpackbits(host["bits"][:(total_bits + 7) // 8])[:total_bits] + np.uint8(48)
     return host
 
 

@@ -167,6 +167,18 @@ def _forced_groups(starts_host_per_segment, table, device):
     return _Groups(starts, group_seed, gid, seg_off_dev, seg_off_host)
 
 
+def to_host(tensors):
+    """Device tensors -> numpy arrays through pinned staging buffers (torch's caching host allocator
+    recycles them), all copies asynchronous on the current stream, ONE synchronisation."""
+    staged = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        staged.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() for h in staged]
+
+
 def bits_to_ascii(bits_host, n_bits, bit_begin=0):
     """Packed MSB-first bits -> the reference's '0'/'1' byte string (BIO:76-79 in reverse)."""
     if n_bits == 0:
