@@ -63,6 +63,8 @@ SIGNATURES = {
     "cwq_fixed_pack": (ctypes.c_int, [_P, _I64, _I32, _P, _SZ, _P]),
     "cwq_fixed_unpack": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     "cwq_elias_delta_parse_host": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
+    "cwq_ac_encode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _P, _I64, _P]),
+    "cwq_ac_decode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     "cwq_draw_candidates": (ctypes.c_int, [_U32, _U32, _U32, _U32, _P, _P]),
     "cwq_stream_words": (ctypes.c_int, [_U32, _U32, _U32, _U32, _P, _P]),
     "cwq_philox4x32_10": (ctypes.c_int, [_P, _P, _P, _I64, _P]),

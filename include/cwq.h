@@ -152,6 +152,16 @@ CWQ_API int cwq_fixed_unpack(const uint8_t* bits, int64_t count, int32_t bits_pe
 CWQ_API int cwq_elias_delta_parse_host(const uint8_t* h_ascii_bits, int64_t n_bits, int64_t n_codes, uint32_t* h_index,
                                int64_t* h_bits_consumed);
 
+/* ---- arithmetic coder of the side information (HOST functions; reference code/coding.pyx) ------
+ * counts[n_symbols] > 0 are the empirical histogram (coding.pyx:29-55); messages end with symbol 0
+ * (coding.pyx:180).  Bits are '0'/'1' bytes as everywhere at the reference boundary.
+ * encode: coding.pyx:59-125.  decode: fast = 0 -> coding.pyx:129-216, fast = 1 -> coding.pyx:220-310. */
+CWQ_API int cwq_ac_encode_host(const int64_t* h_counts, int32_t n_symbols, const int64_t* h_message, int64_t n_message,
+                       int32_t precision, uint8_t* h_ascii_bits, int64_t capacity, int64_t* h_n_bits);
+CWQ_API int cwq_ac_decode_host(const int64_t* h_counts, int32_t n_symbols, const uint8_t* h_ascii_bits, int64_t n_bits,
+                       int32_t precision, int32_t fast, int64_t* h_message, int64_t capacity, int64_t* h_n_message,
+                       int64_t* h_bits_used);
+
 /* ---- the candidate stream (debug / oracle injection seam, misc.py:3-17) ---------------------- */
 /* rows k0..k0+nk-1, G columns, of the N(0,1) table of stream `stream_seed`: out[nk * G] */
 CWQ_API int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, float* out, void* stream);
