@@ -329,9 +329,15 @@ def main():
         "unit": "Tinstr/s", "frac": achieved / issue_peak,
         "sfu_frac": cd_per_s_kernel * SFU_PER_CD / sfu_peak,
         "frac_at_observed_clock": (achieved / (sms * 128 * f_obs)) if f_obs else None,
+        # ideal-independent-chains microbenchmark of this instruction mix: 26.7 cycles per warp-candidate-dim per
+        # sub-partition (tools/microbench/overlap.cu "kernel mix", profiles/r01_pipe_overlap_microbench.log)
+        "frac_of_measured_mix_ceiling": cd_per_s_kernel / (sms * 4 * 32 / 26.7 * f_max),
         "candidate_dims_per_sec_kernel": cd_per_s_kernel, "kernel_ms": score_ms_max,
         "kernel_share_of_step": score_ms_max / ms_per_step if ms_per_step > 0 else None,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on a 2-image
+        # launch (4 046 592 B read, 0 B written; profiles/r01_is_score_ncu_summary.md), scaled to this launch's images
+        "traffic": 4046592.0 * args.images / 2.0 / (world if world > 1 else 1),
+        "algorithmic_bytes": 8.0 * n_total / world + 16.0 * n_groups / world,
         "peak_source": "{} SMs x 128 FP32 lanes x {:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); the path is on-chip "
                        "issue/SFU bound, not HBM or tensor bound (SURVEY.md 8d); pipe widths: profiles/r01_pipes_microbench*.log"
                        .format(sms, f_max / 1e6),
@@ -339,7 +345,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU leg is reported at N = 1 only
         threads = os.cpu_count() or 1
         c = cpu_reference_sample(segs, threads, target_seconds=15.0)
         cpu = {"value": c["groups_per_s"], "unit": UNIT, "cores": threads, "kind": "port", "sample": c["sample"],

@@ -48,6 +48,20 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, 
   ze = __fmul_rn(r, c); zo = __fmul_rn(r, s);
 }
 
+// uniforms through I2FP (FMA-pipe conversion) instead of LOP3 mantissa masks (ALU pipe)
+__device__ __forceinline__ void box_muller_cvt(uint32_t xa, uint32_t xb, float& ze, float& zo) {
+  float fa = __uint2float_rn(xa), fb = __uint2float_rn(xb);
+  float u1 = __fmaf_rn(fa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (x + 0.5) * 2^-32 in (0, 1]
+  float th = __fmaf_rn(fb, 1.4629180792671596e-9f, -3.1415927f);                 // 2 pi * x * 2^-32 - pi
+  float l, r, c, s;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+  float r2 = __fmul_rn(l, -1.3862944f);
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+  ze = __fmul_rn(r, c); zo = __fmul_rn(r, s);
+}
+
 // ---- packed fp32x2 helpers (sm_100: FFMA2 / FMUL2) ----
 typedef unsigned long long f2x;
 __device__ __forceinline__ f2x pack2(float a, float b) { f2x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -116,8 +130,8 @@ __global__ void __launch_bounds__(256, MINB) k_loop(uint32_t* out, uint32_t seed
         uint32_t o[4];
         if (V == 0) block<false>(k, q, seed, o); else block<true>(k, q, seed, o);
         float z[4];
-        box_muller(o[0], o[1], z[0], z[1]);
-        box_muller(o[2], o[3], z[2], z[3]);
+        if (V == 7) { box_muller_cvt(o[0], o[1], z[0], z[1]); box_muller_cvt(o[2], o[3], z[2], z[3]); }
+        else { box_muller(o[0], o[1], z[0], z[1]); box_muller(o[2], o[3], z[2], z[3]); }
         float4 c01 = V == 3 ? rc[2 * q] : sc[2 * q], c23 = V == 3 ? rc[2 * q + 1] : sc[2 * q + 1];
         acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
         acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
@@ -283,12 +297,15 @@ int main() {
     run<2, 1>("V2 asm-mul f32x2 smem", sms, bps, d_out, d_cyc, d_coef);
     run<3, 1>("V3 asm-mul scalar regs", sms, bps, d_out, d_cyc, d_coef);
     run<4, 1>("V4 asm-mul f32x2 regs", sms, bps, d_out, d_cyc, d_coef);
+    run<7, 1>("V7 asm-mul I2FP uniforms", sms, bps, d_out, d_cyc, d_coef);
   }
   run5<5, 1>("V5 sw-pipelined scalar", sms, 2, d_out, d_cyc, d_coef);
   run5<5, 3>("V5 sw-pipelined scalar minb3", sms, 3, d_out, d_cyc, d_coef);
   run5<5, 4>("V5 sw-pipelined scalar minb4", sms, 4, d_out, d_cyc, d_coef);
   // register-capped builds
   run<1, 4>("V1 minb4", sms, 4, d_out, d_cyc, d_coef);
+  run<7, 4>("V7 minb4", sms, 4, d_out, d_cyc, d_coef);
+  run<7, 3>("V7 minb3", sms, 3, d_out, d_cyc, d_coef);
   run<2, 4>("V2 minb4", sms, 4, d_out, d_cyc, d_coef);
   run<1, 6>("V1 minb6", sms, 6, d_out, d_cyc, d_coef);
   run<2, 6>("V2 minb6", sms, 6, d_out, d_cyc, d_coef);

@@ -80,5 +80,9 @@ int main() {
   run<18, 0, 0, 25>("kernel mix / 5 cd, W+F", sms, d_out);
   run<18, 10, 0, 0>("kernel mix / 5 cd, W+M", sms, d_out);
   run<9, 5, 4, 12>("kernel mix / 2.5 cd", sms, d_out);
+  // 3 Philox blocks per 16 dims instead of 4 (radius words + shared angle word): 44 instead of 58 IMAD.WIDE per candidate
+  run<14, 10, 9, 25>("3-block mix / 5 cd", sms, d_out);
+  run<14, 10, 10, 25>("3-block mix / 5 cd, +3 ALU", sms, d_out);
+  run<14, 10, 9, 23>("3-block mix / 5 cd, -2 FP", sms, d_out);
   return 0;
 }
