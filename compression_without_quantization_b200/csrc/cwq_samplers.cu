@@ -11,6 +11,7 @@
 #include "cwq_common.cuh"
 #include "cwq_spec.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace cwq {
 
@@ -468,6 +469,10 @@ static int ensure_device_props() {
   CWQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score, IS_THREADS, 0));
   g_is_blocks_per_sm = bps > 0 ? bps : 1;
+  if (const char* e = getenv("CWQ_IS_BLOCKS_PER_SM")) {   // tuning knob: fewer resident CTAs than the occupancy limit
+    int v = atoi(e);
+    if (v >= 1 && v <= g_is_blocks_per_sm) g_is_blocks_per_sm = v;
+  }
   g_sm_count = sms;
   return CWQ_OK;
 }

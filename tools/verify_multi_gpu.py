@@ -1,0 +1,50 @@
+"""torchrun --nproc-per-node N tools/verify_multi_gpu.py : the sharded encode (contiguous work-balanced group
+ranges + all-gather of indices) returns, on every rank, exactly what the single-GPU encode returns."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import compression_without_quantization_b200 as cwq  # noqa: E402
+from compression_without_quantization_b200 import distributed as D  # noqa: E402
+from compression_without_quantization_b200.synthetic import Normal, synthetic_posterior  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+sizes = [196608, 2304, 50000, 1]
+data = [synthetic_posterior(n, 300 + i, i % 2 == 1) for i, n in enumerate(sizes)]
+t = [Normal(d[0], d[1]) for d in data]
+p = [Normal(d[2], d[3]) for d in data]
+mg = [4, 2, 3, 4]
+
+
+def digest(res):
+    h = hashlib.sha256()
+    for s, code, starts, (oi, oq) in res:
+        for a in (s, starts, oi, oq):
+            h.update(np.ascontiguousarray(a).tobytes())
+        h.update(code)
+    return h.hexdigest()
+
+
+sharded = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard())
+single = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12)
+ok_is = digest(sharded) == digest(single)
+gs = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6, shard=D.make_greedy_shard())
+g1 = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6)
+ok_gr = all(a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) for a, b in zip(gs, g1))
+flags = torch.tensor([int(ok_is), int(ok_gr)], device="cuda")
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("world", world, "importance sharded == single:", bool(flags[0]), " greedy sharded == single:", bool(flags[1]),
+          " groups:", sum(len(r[2]) - 1 for r in single), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flags.min().item() == 1 else 1)
