@@ -390,3 +390,49 @@ def test_gpu_greedy_sampler_against_reference_goldens(cwq, syn, name):
     assert agree.mean() >= 0.8
     same = np.repeat(agree, np.diff(starts))
     assert np.allclose(s[same], g[name + "_sample"][same], rtol=REL_TOL, atol=3e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes, through size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_bench_batch_24_images_round_trip_and_invariances(cwq, syn):
+    """configs[3]: 24 x (768x512) both levels.  decode(encode) reproduces the latents bit for bit outside
+    outliers; the batch equals its first image coded alone; bitstream length == sum of Elias-delta lengths."""
+    from compression_without_quantization_b200 import engine as E
+    n1, n2 = syn.pln_level_sizes(512, 768)
+    data, mg = [], []
+    for img in range(24):
+        data += [syn.synthetic_posterior(n2, 1000 + img), syn.synthetic_posterior(n1, img)]
+        mg += [2, 4]
+    t = [syn.Normal(d[0], d[1]) for d in data]
+    p = [syn.Normal(d[2], d[3]) for d in data]
+    res = cwq.code_grouped_importance_sample_batch(t, p, 42, 20, mg, 16)
+    assert sum(len(r[2]) - 1 for r in res) > 300000
+    dec = cwq.decode_grouped_importance_sample_batch([r[1] for r in res], [list(r[2]) for r in res], p, 42,
+                                                     [r[3][0] for r in res], [r[3][1] for r in res])
+    for r, d, dat in zip(res, dec, data):
+        inl = np.ones(d.size, bool)
+        inl[r[3][0]] = False
+        assert np.array_equal(d[inl].view(np.uint32), r[0][inl].view(np.uint32))
+        ng = len(r[2]) - 1
+        idx, used = E.elias_delta_parse(r[1], ng)
+        assert used == len(r[1])
+        head = ''.join(cwq.elias_delta_code(int(i) + 1) for i in idx[:200]).encode()
+        assert r[1][:len(head)] == head
+    one = cwq.code_grouped_importance_sample_batch(t[:2], p[:2], 42, 20, mg[:2], 16)
+    for a, b in zip(one, res[:2]):
+        assert a[1] == b[1] and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[2], b[2])
+
+
+def test_full_image_greedy_defaults_round_trip(cwq, syn):
+    """configs[0]: one 768x512 image, level 1, reference defaults (30 steps x 2^14 candidates, groups <= 4095)."""
+    n1, _ = syn.pln_level_sizes(512, 768)
+    q_loc, q_scale, p_loc, p_scale = syn.synthetic_posterior(n1, 0, True)
+    prop = syn.Normal(p_loc, p_scale)
+    sample, code, starts = cwq.code_grouped_greedy_sample(None, syn.Normal(q_loc, q_scale), prop, 30, 14, 42, 12)
+    assert starts[-1] == n1 and len(code) == (len(starts) - 1) * 30 * 14 and max(np.diff(starts)) <= 4095
+    dec = cwq.decode_grouped_greedy_sample(None, code, starts[:-1], prop, 14, 30, 42)
+    assert np.array_equal(dec.view(np.uint32), sample.view(np.uint32))
+    # the coded sample is close to the posterior: average squared standardised error well below the prior's
+    zq = (sample - q_loc) / q_scale
+    assert np.mean(zq ** 2) < 3.0
