@@ -55,7 +55,8 @@ SIGNATURES = {
     "cwq_outlier_workspace_bytes": (_SZ, [_I64]),
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "cwq_outlier_decode": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
-    "cwq_greedy_encode": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _F32, _I64, _P, _P, _P]),
+    "cwq_greedy_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
+    "cwq_greedy_encode": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _F32, _I64, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "cwq_greedy_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _F32, _P, _P, _P, _P]),
     "cwq_unrescale": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
     "cwq_pack_workspace_bytes": (_SZ, [_I64]),

@@ -325,12 +325,15 @@ class GreedyJob:
         self.max_group_size = int(sizes.max().item())
         return self
 
-    def encode(self, g0=0, g1=None):
+    def encode(self, g0=0, g1=None, mode=0):
+        """mode 0: automatic; 1: one persistent CTA per group; 2: lockstep units (few groups)."""
         ng = self.groups.n_groups
         g1 = ng if g1 is None else g1
+        wsb = _lib.load().cwq_greedy_workspace_bytes(self.n, ng, self.n_steps)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
         _lib.call("cwq_greedy_encode", _ptr(self.tparam), _ptr(self.groups.starts), _ptr(self.groups.group_seed), ng, g0, g1,
-                  self.n_steps, self.n_bits_per_step, self.shard_scale, self.max_group_size, _ptr(self.indices),
-                  _ptr(self.best), _stream())
+                  self.n_steps, self.n_bits_per_step, self.shard_scale, self.max_group_size, self.n, int(mode),
+                  _ptr(self.indices), _ptr(self.best), _ptr(ws), wsb, _stream())
         return self
 
     def decode(self):

@@ -124,11 +124,15 @@ CWQ_API int cwq_outlier_decode(float* sample, const int64_t* outlier_pos, const 
                        void* stream);
 
 /* ---- greedy sampler --------------------------------------------------------------------------
- * CGS:38-78 for groups [g0, g1): n_steps sequential steps of 2^n_bits_per_step candidates each,
- * one persistent CTA per group.  indices[g * n_steps + j]; best[n] in rescaled coordinates. */
+ * CGS:38-78 for groups [g0, g1): n_steps sequential steps of 2^n_bits_per_step candidates each.
+ * mode 1: one persistent CTA per group, step state on chip (many groups); mode 2: all groups in lockstep,
+ * (group, 1024-candidate) units claimed dynamically, two grid barriers per step (few groups, e.g. one
+ * image); mode 0 picks.  Identical results.  indices[g * n_steps + j]; best[n] in rescaled coordinates. */
+CWQ_API size_t cwq_greedy_workspace_bytes(int64_t n, int64_t n_groups, int32_t n_steps);
 CWQ_API int cwq_greedy_encode(const float* tparam, const int64_t* starts, const uint32_t* group_seed, int64_t n_groups,
                       int64_t g0, int64_t g1, int32_t n_steps, int32_t n_bits_per_step, float shard_scale,
-                      int64_t max_group_size, uint32_t* indices, float* best, void* stream);
+                      int64_t max_group_size, int64_t n, int32_t mode, uint32_t* indices, float* best,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* CGS:134-165 + CGS:292/362: replay the chosen rows and un-rescale. */
 CWQ_API int cwq_greedy_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid,
                       const uint32_t* indices, int64_t n, int32_t n_steps, float shard_scale, const float* p_loc,

@@ -436,3 +436,27 @@ def test_full_image_greedy_defaults_round_trip(cwq, syn):
     # the coded sample is close to the posterior: average squared standardised error well below the prior's
     zq = (sample - q_loc) / q_scale
     assert np.mean(zq ** 2) < 3.0
+
+
+def test_greedy_kernel_variants_agree(cwq, syn):
+    """mode 1 (one persistent CTA per group) and mode 2 (lockstep units, cooperative launch) give identical
+    indices and latents; mode 0 picks by group count."""
+    import torch
+    from compression_without_quantization_b200 import engine as E
+    n = 9000
+    arrs = syn.synthetic_posterior(n, 61, True)
+    dev = E.cuda_device()
+    outs = []
+    for mode in (1, 2, 0):
+        job = E.GreedyJob(*(torch.from_numpy(x).to(dev) for x in arrs), [E.SegmentSpec(n, 42, 5 * 9, 6, float("inf"), False)], 5, 9)
+        job.prepare().encode(mode=mode)
+        outs.append((job.indices.cpu().numpy().copy(), job.best.cpu().numpy().copy()))
+    for idx, best in outs[1:]:
+        assert np.array_equal(idx, outs[0][0]) and np.array_equal(best.view(np.uint32), outs[0][1].view(np.uint32))
+    # a partial group range leaves the other groups untouched
+    job = E.GreedyJob(*(torch.from_numpy(x).to(dev) for x in arrs), [E.SegmentSpec(n, 42, 5 * 9, 6, float("inf"), False)], 5, 9).prepare()
+    ng = job.groups.n_groups
+    job.encode(ng // 3, 2 * ng // 3, mode=2)
+    idx = job.indices.cpu().numpy().reshape(ng, 5)
+    assert np.array_equal(idx[ng // 3:2 * ng // 3], outs[0][0].reshape(ng, 5)[ng // 3:2 * ng // 3])
+    assert not idx[:ng // 3].any() and not idx[2 * ng // 3:].any()

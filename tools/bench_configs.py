@@ -47,7 +47,7 @@ def is_config(name, arrays, specs, reps):
                       "candidate_dims_per_s": cd / ms * 1e3}), flush=True)
 
 
-def greedy_config(name, arrays, specs, n_steps, n_bits, reps, g_limit=None):
+def greedy_config(name, arrays, specs, n_steps, n_bits, reps, g_limit=None, mode=0):
     dev = E.cuda_device()
     t = [torch.from_numpy(np.concatenate(a)).to(dev) for a in zip(*arrays)]
     job = E.GreedyJob(t[0], t[1], t[2], t[3], specs, n_steps, n_bits).prepare()
@@ -55,7 +55,7 @@ def greedy_config(name, arrays, specs, n_steps, n_bits, reps, g_limit=None):
     g1 = ng if g_limit is None else min(ng, g_limit)
 
     def run():
-        job.encode(0, g1)
+        job.encode(0, g1, mode=mode)
         return job
     ms, _ = timed(run, reps)
     sizes = (job.groups.starts[1:g1 + 1] - job.groups.starts[:g1]).double()
@@ -92,6 +92,13 @@ def main():
         specs = [E.SegmentSpec(m1, 42, 30 * 14, 12, float("inf"), False)]
         greedy_config("configs[4] slice: one 3840x2160 image level 1, greedy 30 x 2^14, first 1184 groups", arrays, specs, 30, 14, 1,
                       g_limit=1184)
+    if want("c4modes"):
+        m1, _ = pln_level_sizes(2160, 3840)
+        arrays = [synthetic_posterior(m1, 5)]
+        specs = [E.SegmentSpec(m1, 42, 30 * 14, 12, float("inf"), False)]
+        for mode in (1, 2):
+            greedy_config("configs[4] one 3840x2160 image, all 7535 groups, mode {}".format(mode), arrays, specs, 30, 14, 1, mode=mode)
+            greedy_config("configs[4] slice 1184 groups, mode {}".format(mode), arrays, specs, 30, 14, 1, g_limit=1184, mode=mode)
 
 
 if __name__ == "__main__":
