@@ -217,11 +217,11 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs).prepare()
+        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs).prepare(sync=world > 1)
         if world > 1:
-            D.make_is_shard()(job)
+            D.make_is_shard()(job)     # needs the per-group work on the host: one synchronisation after grouping
         else:
-            job.encode()
+            job.encode()               # N = 1: no host synchronisation anywhere inside the step
         job.decode().pack()
         return job
 
@@ -233,6 +233,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         job = step_device()
     barrier()
+    job.sync_groups()
     n_groups = job.groups.n_groups
     sizes = (job.groups.starts[1:] - job.groups.starts[:-1]).to(torch.float64)
     Kd = job.K.to(torch.float64)

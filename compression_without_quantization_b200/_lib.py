@@ -48,9 +48,9 @@ SIGNATURES = {
     "cwq_group_workspace_bytes": (_SZ, [_I64, _I32]),
     "cwq_group": (ctypes.c_int, [_P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "cwq_expand_groups": (ctypes.c_int, [_P, _I64, _I64, _P, _I32, _P, _P, _P, _P]),
-    "cwq_group_totals": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "cwq_group_totals": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "cwq_is_encode_workspace_bytes": (_SZ, [_I64]),
-    "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _SZ, _P]),
+    "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _SZ, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "cwq_outlier_workspace_bytes": (_SZ, [_I64]),
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -60,7 +60,7 @@ SIGNATURES = {
     "cwq_greedy_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _F32, _P, _P, _P, _P]),
     "cwq_unrescale": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
     "cwq_pack_workspace_bytes": (_SZ, [_I64]),
-    "cwq_elias_delta_pack": (ctypes.c_int, [_P, _I64, _P, _SZ, _P, _P, _SZ, _P]),
+    "cwq_elias_delta_pack": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P, _P, _SZ, _P]),
     "cwq_fixed_pack": (ctypes.c_int, [_P, _I64, _I32, _P, _SZ, _P]),
     "cwq_fixed_unpack": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     "cwq_elias_delta_parse_host": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),

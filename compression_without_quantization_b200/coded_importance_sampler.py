@@ -105,17 +105,17 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
     sizes = [int(x.numel()) for x in p_loc]
     specs = [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
     cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
-    job = E.ISJob(cat(q_loc), cat(q_scale), cat(p_loc), cat(p_scale), specs).prepare()
+    job = E.ISJob(cat(q_loc), cat(q_scale), cat(p_loc), cat(p_scale), specs).prepare(sync=shard is not None)
     if stage == "groups":
-        return job
+        return job.sync_groups()
     if shard is None:
-        job.encode()
+        job.encode()          # nothing below waits for the host until the results are copied back
     else:
         shard(job)
     if stage == "indices":
-        return job
+        return job.sync_groups()
     job.decode().pack()
-    return job
+    return job.sync_groups()
 
 
 def _segment_result(job, s, host, return_indices):

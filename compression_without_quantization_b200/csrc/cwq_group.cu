@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(256) k_group_seed(const long long* __restrict_
 }
 
 __global__ void __launch_bounds__(256) k_group_totals(const float* __restrict__ kl, const long long* __restrict__ starts,
-                                                      long long n_groups, float* __restrict__ total_kl, int* __restrict__ K) {
+                                                      long long n_groups, const long long* __restrict__ ng_dev,
+                                                      float* __restrict__ total_kl, int* __restrict__ K) {
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ng_dev) n_groups = *ng_dev;
   if (g >= n_groups) return;
   float acc = 0.0f;
   for (long long i = starts[g], e = starts[g + 1]; i < e; ++i) acc = __fadd_rn(acc, kl[i]);
@@ -369,11 +371,11 @@ extern "C" int cwq_expand_groups(const int64_t* starts, int64_t n_groups, int64_
   return CWQ_OK;
 }
 
-extern "C" int cwq_group_totals(const float* kl, const int64_t* starts, int64_t n_groups, float* total_kl, int32_t* K,
-                                void* stream) {
+extern "C" int cwq_group_totals(const float* kl, const int64_t* starts, int64_t n_groups, const int64_t* n_groups_dev,
+                                float* total_kl, int32_t* K, void* stream) {
   CWQ_REQUIRE(n_groups > 0, "n_groups must be positive");
   k_group_totals<<<(unsigned)((n_groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kl, (const long long*)starts, n_groups,
-                                                                                      total_kl, K);
+                                                                                      (const long long*)n_groups_dev, total_kl, K);
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }

@@ -26,22 +26,29 @@ constexpr int IS_WARPS = IS_THREADS / 32;
 constexpr int UNIT_CAND = 1024;  // candidates per unit
 constexpr int UNIT_BATCH = 4;    // units claimed per atomic
 
+// ng_dev (optional): the group count lives on the device and `ng` passed by the host is only a capacity
 struct UnitCount {
   const int* K;
   long long g0;
-  __device__ ull operator()(long long j) const { return (ull)((K[g0 + j] + UNIT_CAND - 1) / UNIT_CAND); }
+  const long long* ng_dev;
+  __device__ ull operator()(long long j) const {
+    if (ng_dev && j >= *ng_dev) return 0ull;
+    return (ull)((K[g0 + j] + UNIT_CAND - 1) / UNIT_CAND);
+  }
 };
 struct UnitDeliver {
   ull* unit_off;
   ull* keys;
   long long g0;
+  const long long* ng_dev;
   __device__ void operator()(long long j, ull pre, ull) const {
+    if (ng_dev && j >= *ng_dev) return;
     unit_off[j] = pre;
     keys[g0 + j] = KEY_INIT;
   }
 };
-__global__ void k_units_finish(ull* unit_off, long long ng, const ull* total, ull* counter) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { unit_off[ng] = *total; *counter = 0; }
+__global__ void k_units_finish(ull* unit_off, long long ng, const long long* ng_dev, const ull* total, ull* counter) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { unit_off[ng_dev ? *ng_dev : ng] = *total; *counter = 0; }
 }
 
 __device__ __forceinline__ ull warp_max_key(ull key) {
@@ -105,10 +112,12 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 
 __global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
-                                                         long long g0, long long ng, const ull* __restrict__ unit_off,
+                                                         long long g0, long long ng, const long long* __restrict__ ng_dev,
+                                                         const ull* __restrict__ unit_off,
                                                          ull* __restrict__ counter, ull* __restrict__ keys) {
   __shared__ float4 s_coef[IS_WARPS][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (ng_dev) ng = *ng_dev;
   const ull n_units = unit_off[ng];
   float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
   for (;;) {
@@ -161,8 +170,9 @@ __global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restric
 }
 
 __global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, long long g0, long long g1,
-                                                  uint32_t* __restrict__ index) {
+                                                  const long long* __restrict__ ng_dev, uint32_t* __restrict__ index) {
   long long g = g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ng_dev) g1 = *ng_dev;
   if (g < g1) index[g] = key_index(keys[g]);
 }
 
@@ -494,7 +504,9 @@ __device__ __forceinline__ void elias_delta(uint32_t x, ull& pattern, int& len) 
 
 struct EliasLen {
   const uint32_t* index;
+  const long long* ng_dev;
   __device__ ull operator()(long long g) const {
+    if (ng_dev && g >= *ng_dev) return 0ull;
     ull p; int len;
     elias_delta(index[g] + 1u, p, len);
     return (ull)len;
@@ -504,15 +516,17 @@ struct EliasDeliver {
   const uint32_t* index;
   long long* bit_off;
   uint32_t* words;
+  const long long* ng_dev;
   __device__ void operator()(long long g, ull pre, ull) const {
+    if (ng_dev && g >= *ng_dev) return;
     ull p; int len;
     elias_delta(index[g] + 1u, p, len);
     bit_off[g] = (long long)pre;
     put_bits(words, pre, p, len);
   }
 };
-__global__ void k_bits_finish(long long* bit_off, long long ng, const ull* total) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) bit_off[ng] = (long long)*total;
+__global__ void k_bits_finish(long long* bit_off, long long ng, const long long* ng_dev, const ull* total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) bit_off[ng_dev ? *ng_dev : ng] = (long long)*total;
 }
 __global__ void __launch_bounds__(256) k_bswap_words(uint32_t* __restrict__ words, long long nw) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -646,9 +660,10 @@ extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
 }
 
 extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
-                             int64_t n_groups, int64_t g0, int64_t g1, uint32_t* index, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, uint32_t* index,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
+  CWQ_REQUIRE(!n_groups_dev || (g0 == 0 && g1 == n_groups), "a device-side group count needs the full range [0, capacity)");
   if (g0 == g1) return CWQ_OK;
   int rc = ensure_device_props();
   if (rc != CWQ_OK) return rc;
@@ -661,18 +676,19 @@ extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int
   ull* total = ws.take<ull>(1);
   ull* counter = ws.take<ull>(1);
   if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
-  UnitCount in{K, g0};
-  UnitDeliver out{unit_off, keys, g0};
+  const long long* ngd = (const long long*)n_groups_dev;
+  UnitCount in{K, g0, ngd};
+  UnitDeliver out{unit_off, keys, g0, ngd};
   CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, ng, tile_sums, total, st)));
-  k_units_finish<<<1, 32, 0, st>>>(unit_off, ng, total, counter);
+  k_units_finish<<<1, 32, 0, st>>>(unit_off, ng, ngd, total, counter);
   CWQ_LAUNCH_CHECK();
   const bool prof = g_profile && g_profile_count < PROFILE_RING;
   if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
   k_is_score<<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K, group_seed,
-                                                                     g0, ng, unit_off, counter, keys);
+                                                                     g0, ng, ngd, unit_off, counter, keys);
   CWQ_LAUNCH_CHECK();
   if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
-  k_is_index<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(keys, g0, g1, index);
+  k_is_index<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(keys, g0, g1, ngd, index);
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }
@@ -794,8 +810,9 @@ extern "C" size_t cwq_pack_workspace_bytes(int64_t n_groups) {
   return align_up((size_t)scan_tiles(n_groups) * 8) + 1024;
 }
 
-extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, uint8_t* bits, size_t bits_capacity_bytes,
-                                    int64_t* bit_off, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, const int64_t* n_groups_dev, uint8_t* bits,
+                                    size_t bits_capacity_bytes, int64_t* bit_off, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   CWQ_REQUIRE(n_groups > 0, "n_groups must be positive");
   CWQ_REQUIRE(bits_capacity_bytes % 4 == 0 && bits_capacity_bytes >= ((size_t)n_groups * 42 + 31) / 32 * 4,
               "bits capacity must be a multiple of 4 and hold 42 bits per group");
@@ -805,10 +822,11 @@ extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, uin
   ull* total = ws.take<ull>(1);
   if (!tile_sums || !total) { set_error("cwq_elias_delta_pack: workspace too small"); return CWQ_ERR_WORKSPACE; }
   CWQ_CUDA(cudaMemsetAsync(bits, 0, bits_capacity_bytes, st));
-  EliasLen in{index};
-  EliasDeliver out{index, (long long*)bit_off, (uint32_t*)bits};
+  const long long* ngd = (const long long*)n_groups_dev;
+  EliasLen in{index, ngd};
+  EliasDeliver out{index, (long long*)bit_off, (uint32_t*)bits, ngd};
   CWQ_CUDA((device_exclusive_scan<ull, EliasLen, EliasDeliver>(in, out, n_groups, tile_sums, total, st)));
-  k_bits_finish<<<1, 32, 0, st>>>((long long*)bit_off, n_groups, total);
+  k_bits_finish<<<1, 32, 0, st>>>((long long*)bit_off, n_groups, ngd, total);
   CWQ_LAUNCH_CHECK();
   long long nw = (long long)(bits_capacity_bytes / 4);
   k_bswap_words<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((uint32_t*)bits, nw);

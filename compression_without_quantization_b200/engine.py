@@ -118,18 +118,43 @@ class SegmentTable:
 
 
 class _Groups:
-    """Group tables on the device (+ the per-segment offsets on the host)."""
+    """Group tables on the device.  After cwq_group the group count is known only on the device
+    (`n_groups_dev`); `sync()` brings it and the per-segment offsets to the host and trims the views."""
 
-    def __init__(self, starts, group_seed, gid, seg_group_off, seg_group_off_host):
+    def __init__(self, starts, group_seed, gid, seg_group_off, seg_group_off_host=None, capacity=None):
         self.starts = starts
         self.group_seed = group_seed
         self.gid = gid
         self.seg_group_off = seg_group_off
         self.seg_group_off_host = seg_group_off_host
-        self.n_groups = int(seg_group_off_host[-1])
+        self.capacity = capacity if capacity is not None else int(group_seed.numel())
+        self.n_groups_dev = seg_group_off[-1:]          # int64 scalar on the device
+        self._n_groups = None if seg_group_off_host is None else int(seg_group_off_host[-1])
+
+    @property
+    def synced(self):
+        return self._n_groups is not None
+
+    @property
+    def n_groups(self):
+        if self._n_groups is None:
+            self.sync()
+        return self._n_groups
+
+    def sync(self):
+        if self._n_groups is None:
+            self.seg_group_off_host = self.seg_group_off.cpu().numpy()
+            self._n_groups = ng = int(self.seg_group_off_host[-1])
+            self.starts = self.starts[:ng + 1]
+            self.group_seed = self.group_seed[:ng]
+        return self
 
 
-def _run_group(kl, table):
+# above this many dims the capacity-sized scratch of the synchronisation-free pipeline is not worth its memory
+ASYNC_MAX_DIMS = 1 << 25
+
+
+def _run_group(kl, table, sync=True):
     dev = kl.device
     n, ns = table.n, table.count
     starts = torch.empty(n + ns + 1, dtype=torch.int64, device=dev)
@@ -140,9 +165,8 @@ def _run_group(kl, table):
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     _lib.call("cwq_group", _ptr(kl), n, _ptr(table.dev), ctypes.cast(table.host, ctypes.c_void_p), ns, _ptr(starts),
               _ptr(group_seed), _ptr(gid), _ptr(seg_off), _ptr(ws), wsb, _stream())
-    seg_off_host = seg_off.cpu().numpy()  # the one mid-pipeline host sync: n_groups sizes everything after
-    ng = int(seg_off_host[-1])
-    return _Groups(starts[:ng + 1], group_seed[:ng], gid, seg_off, seg_off_host)
+    g = _Groups(starts, group_seed, gid, seg_off, None, capacity=n + ns)
+    return g.sync() if sync else g
 
 
 def _forced_groups(starts_host_per_segment, table, device):
@@ -164,7 +188,7 @@ def _forced_groups(starts_host_per_segment, table, device):
     group_seed = torch.empty(ng, dtype=torch.int32, device=device)
     _lib.call("cwq_expand_groups", _ptr(starts), ng, table.n, _ptr(table.dev), table.count, _ptr(seg_off_dev), _ptr(gid),
               _ptr(group_seed), _stream())
-    return _Groups(starts, group_seed, gid, seg_off_dev, seg_off_host)
+    return _Groups(starts, group_seed, gid, seg_off_dev, seg_off_host, capacity=ng)
 
 
 def to_host(tensors):
@@ -216,32 +240,58 @@ class ISJob:
         self.forced_starts = forced_starts
         self.groups = None
 
-    def prepare(self):
+    def prepare(self, sync=True):
+        """Prologue, grouping, candidate counts.  sync=False keeps the group count on the device so that
+        encode()/decode()/pack() are enqueued without waiting for the grouping; per-group arrays then have
+        capacity N + n_segments until sync_groups() trims them (used by the batch API for N <= 2^25)."""
         n, t = self.n, self.table
+        if n > ASYNC_MAX_DIMS:
+            sync = True
         self.kl = torch.empty(n, dtype=torch.float32, device=self.dev)
         self.coef = torch.empty(2 * n, dtype=torch.float32, device=self.dev)
         self.mask = torch.empty(n, dtype=torch.uint8, device=self.dev)
         _lib.call("cwq_is_prologue", _ptr(self.q_loc), _ptr(self.q_scale), _ptr(self.p_loc), _ptr(self.p_scale), n,
                   _ptr(t.dev), t.count, _ptr(self.kl), _ptr(self.coef), _ptr(self.mask), _stream())
         if self.forced_starts is None:
-            self.groups = _run_group(self.kl, t)
+            self.groups = _run_group(self.kl, t, sync=sync)
         else:
             self.groups = _forced_groups(self.forced_starts, t, self.dev)
-        ng = self.groups.n_groups
-        self.total_kl = torch.empty(ng, dtype=torch.float32, device=self.dev)
-        self.K = torch.empty(ng, dtype=torch.int32, device=self.dev)
-        _lib.call("cwq_group_totals", _ptr(self.kl), _ptr(self.groups.starts), ng, _ptr(self.total_kl), _ptr(self.K),
-                  _stream())
-        self.index = torch.zeros(ng, dtype=torch.int32, device=self.dev)  # uint32 payload
+        cap = self.groups.n_groups if self.groups.synced else self.groups.capacity
+        self._cap = cap
+        self.total_kl = torch.empty(cap, dtype=torch.float32, device=self.dev)
+        self.K = torch.empty(cap, dtype=torch.int32, device=self.dev)
+        _lib.call("cwq_group_totals", _ptr(self.kl), _ptr(self.groups.starts), cap, self._ng_dev(), _ptr(self.total_kl),
+                  _ptr(self.K), _stream())
+        self.index = torch.zeros(cap, dtype=torch.int32, device=self.dev)  # uint32 payload
         return self
 
-    def encode(self, g0=0, g1=None):
+    def _ng_dev(self):
+        return ctypes.c_void_p(0) if self.groups.synced else _ptr(self.groups.n_groups_dev)
+
+    def sync_groups(self):
+        """Make the group count known on the host (one device->host copy) and trim the per-group arrays."""
+        if not self.groups.synced:
+            self.groups.sync()
         ng = self.groups.n_groups
-        g1 = ng if g1 is None else g1
-        wsb = _lib.load().cwq_is_encode_workspace_bytes(ng)
+        for name in ("total_kl", "K", "index"):
+            if hasattr(self, name) and getattr(self, name).numel() != ng:
+                setattr(self, name, getattr(self, name)[:ng])
+        if hasattr(self, "bit_off") and self.bit_off.numel() != ng + 1:
+            self.bit_off = self.bit_off[:ng + 1]
+        self._cap = ng
+        return self
+
+    def encode(self, g0=None, g1=None):
+        """Score groups [g0, g1) (default: all).  A partial range needs the host-side count and synchronises."""
+        if g0 is not None or g1 is not None:
+            self.sync_groups()
+        cap = self._cap
+        g0 = 0 if g0 is None else g0
+        g1 = cap if g1 is None else g1
+        wsb = _lib.load().cwq_is_encode_workspace_bytes(cap)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
         _lib.call("cwq_is_encode", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
-                  ng, g0, g1, _ptr(self.index), _ptr(ws), wsb, _stream())
+                  cap, self._ng_dev(), g0, g1, _ptr(self.index), _ptr(ws), wsb, _stream())
         return self
 
     def decode(self):
@@ -262,18 +312,19 @@ class ISJob:
         return self
 
     def pack(self):
-        ng = self.groups.n_groups
-        cap = ((ng * 42 + 31) // 32) * 4
+        ngc = self._cap
+        cap = ((ngc * 42 + 31) // 32) * 4
         self.bits = torch.empty(cap, dtype=torch.uint8, device=self.dev)
-        self.bit_off = torch.empty(ng + 1, dtype=torch.int64, device=self.dev)
-        wsb = _lib.load().cwq_pack_workspace_bytes(ng)
+        self.bit_off = torch.empty(ngc + 1, dtype=torch.int64, device=self.dev)
+        wsb = _lib.load().cwq_pack_workspace_bytes(ngc)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
-        _lib.call("cwq_elias_delta_pack", _ptr(self.index), ng, _ptr(self.bits), cap, _ptr(self.bit_off), _ptr(ws), wsb,
-                  _stream())
+        _lib.call("cwq_elias_delta_pack", _ptr(self.index), ngc, self._ng_dev(), _ptr(self.bits), cap, _ptr(self.bit_off),
+                  _ptr(ws), wsb, _stream())
         return self
 
     # ---- host views (each does a device->host copy) ----
     def segment_group_range(self, s):
+        self.sync_groups()
         off = self.groups.seg_group_off_host
         return int(off[s]), int(off[s + 1])
 

@@ -94,17 +94,20 @@ CWQ_API int cwq_group(const float* kl, int64_t n, const cwq_segment* segments, c
 CWQ_API int cwq_expand_groups(const int64_t* starts, int64_t n_groups, int64_t n, const cwq_segment* segments,
                       int32_t n_segments, const int64_t* seg_group_off, int32_t* gid, uint32_t* group_seed,
                       void* stream);
-/* CIS:48-51: total KL of each group (sequential fp32) and K = ceil(exp(total)). */
-CWQ_API int cwq_group_totals(const float* kl, const int64_t* starts, int64_t n_groups, float* total_kl, int32_t* K,
-                     void* stream);
+/* CIS:48-51: total KL of each group (sequential fp32) and K = ceil(exp(total)).
+ * n_groups_dev (here and below, may be NULL): when given, the group count is read on the DEVICE (it is
+ * seg_group_off + n_segments as cwq_group wrote it) and n_groups is only the capacity of the arrays: the
+ * whole encode then runs without a host synchronisation between grouping and scoring. */
+CWQ_API int cwq_group_totals(const float* kl, const int64_t* starts, int64_t n_groups, const int64_t* n_groups_dev,
+                     float* total_kl, int32_t* K, void* stream);
 
 /* ---- importance sampler ----------------------------------------------------------------------
  * CIS:55-63 for groups [g0, g1): index[g] = first candidate maximising the importance weight
  * (0-based; the reference codes index + 1). */
 CWQ_API size_t cwq_is_encode_workspace_bytes(int64_t n_groups);
 CWQ_API int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
-                  int64_t n_groups, int64_t g0, int64_t g1, uint32_t* index, void* workspace,
-                  size_t workspace_bytes, void* stream);
+                  int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, uint32_t* index,
+                  void* workspace, size_t workspace_bytes, void* stream);
 /* CIS:104-109 + CIS:265/347: regenerate row index[g] of every group and un-rescale:
  * sample[i] = p_scale[i] * z + p_loc[i]. */
 CWQ_API int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,
@@ -145,8 +148,9 @@ CWQ_API int cwq_unrescale(const float* best, const float* p_loc, const float* p_
  * BIO:7-20 Elias-delta of index + 1, codes concatenated MSB-first into bytes (the order the '0'/'1'
  * string has in the reference, BIO:76-79).  bit_off[n_groups + 1] = bit offset of each code. */
 CWQ_API size_t cwq_pack_workspace_bytes(int64_t n_groups);
-CWQ_API int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, uint8_t* bits, size_t bits_capacity_bytes,
-                         int64_t* bit_off, void* workspace, size_t workspace_bytes, void* stream);
+CWQ_API int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, const int64_t* n_groups_dev, uint8_t* bits,
+                         size_t bits_capacity_bytes, int64_t* bit_off, void* workspace, size_t workspace_bytes,
+                         void* stream);
 /* BIO:41-53 / CGS:81-87: fixed-width LSB-first codes, concatenated MSB-first into bytes. */
 CWQ_API int cwq_fixed_pack(const uint32_t* index, int64_t count, int32_t bits_per_index, uint8_t* bits,
                    size_t bits_capacity_bytes, void* stream);
