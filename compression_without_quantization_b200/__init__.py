@@ -12,6 +12,6 @@ from .coded_importance_sampler import (code_grouped_importance_sample, code_grou
                                        decode_grouped_importance_sample_batch, decode_importance_sample)
 from .coding import ArithmeticCoder  # noqa: F401
 from .misc import stateless_normal_sample  # noqa: F401
-from .pln_codec import code_image_latents, decode_image_latents, latent_permutations  # noqa: F401
+from .pln_codec import build_empirical_dists, code_image_latents, decode_image_latents, latent_permutations  # noqa: F401
 
 __version__ = "0.1.0"

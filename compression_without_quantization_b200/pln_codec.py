@@ -204,3 +204,52 @@ def decode_image_latents(comp_file_path, synthesis_2, first_level_latent_channel
         decoded1 = decode_grouped_greedy_sample(None, code1, group_indices1[:-1], prior_1, n_bits_per_step, n_steps, seed, rho=rho)
     d1 = _inverse(torch.from_numpy(np.ascontiguousarray(decoded1)).to(dev), perm_1d)
     return (d1.reshape(tuple(first_level_shape)).cpu().numpy(), latents2.cpu().numpy())
+
+
+def build_empirical_dists(images, seed, second_level_n_bits_per_group=20, second_level_max_group_size_bits=4,
+                          second_level_dim_kl_bit_limit=12, first_level_n_bits_per_group=20, first_level_max_group_size_bits=3,
+                          first_level_dim_kl_bit_limit=12, use_permutation=True, with_sample_indices=True):
+    """The histogram part of the reference's `build_empirical_dists` (miracle.py:521-667) without the
+    networks: `images` yields (q1, q2, p2, synthesis_2, second_level_shape) per image; the result is
+    (group_sizes1, group_sizes2, sample_indices1, sample_indices2) int64 count arrays with symbol 0 (the
+    arithmetic coder's end symbol) counted once per image, exactly as miracle.py:621-662 accumulates them.
+    The arithmetic coder needs every count positive (coding.pyx builds a strict search tree), so symbols that
+    never occurred must be smoothed by the caller before use, as in the reference."""
+    dev = E.cuda_device()
+    gs2 = np.zeros(1 + 2 ** second_level_max_group_size_bits, dtype=np.int64)
+    gs1 = np.zeros(1 + 2 ** first_level_max_group_size_bits, dtype=np.int64)
+    si2 = np.zeros(1 + 2 ** second_level_n_bits_per_group, dtype=np.int64) if with_sample_indices else None
+    si1 = np.zeros(1 + 2 ** first_level_n_bits_per_group, dtype=np.int64) if with_sample_indices else None
+    for q1, q2, p2, synthesis_2, second_level_shape in images:
+        q1_loc, q1_scale = _flat32(q1.loc, dev), _flat32(q1.scale, dev)
+        q2_loc, q2_scale = _flat32(q2.loc, dev), _flat32(q2.scale, dev)
+        p2_loc, p2_scale = _flat32(p2.loc, dev), _flat32(p2.scale, dev)
+        n1, n2 = q1_loc.numel(), q2_loc.numel()
+        perm_1, perm_2 = latent_permutations(seed, n1, n2, use_permutation)
+        perm_1d = torch.from_numpy(perm_1.astype(np.int64)).to(dev)
+        perm_2d = torch.from_numpy(perm_2.astype(np.int64)).to(dev)
+        q2p = _Normal(_forward(q2_loc, perm_2d), _forward(q2_scale, perm_2d))
+        p2p = _Normal(_forward(p2_loc, perm_2d), _forward(p2_scale, perm_2d))
+        sample2, idx2, starts2, _ = code_grouped_importance_sample(None, q2p, p2p, seed, second_level_n_bits_per_group,
+                                                                   second_level_max_group_size_bits, second_level_dim_kl_bit_limit,
+                                                                   return_indices=True)
+        u, c = np.unique(np.diff(starts2), return_counts=True)      # miracle.py:621-625
+        gs2[u] += c
+        gs2[0] += 1
+        latents2 = _inverse(torch.from_numpy(np.ascontiguousarray(sample2)).to(dev), perm_2d).reshape(
+            tuple(int(v) for v in second_level_shape))
+        p1_loc_u, p1_scale_u = synthesis_2(latents2)
+        q1p = _Normal(_forward(q1_loc, perm_1d), _forward(q1_scale, perm_1d))
+        p1p = _Normal(_forward(_flat32(p1_loc_u, dev), perm_1d), _forward(_flat32(p1_scale_u, dev), perm_1d))
+        _, idx1, starts1, _ = code_grouped_importance_sample(None, q1p, p1p, seed, first_level_n_bits_per_group,
+                                                             first_level_max_group_size_bits, first_level_dim_kl_bit_limit,
+                                                             return_indices=True)
+        u, c = np.unique(np.diff(starts1), return_counts=True)      # miracle.py:630-636
+        gs1[u] += c
+        gs1[0] += 1
+        if with_sample_indices:
+            for idx, hist in ((idx2, si2), (idx1, si1)):               # miracle.py:645-662 (indices are 1-based, shifted by one)
+                u, c = np.unique(np.asarray(idx, dtype=np.int64), return_counts=True)
+                hist[u + 1] += c
+                hist[0] += 1
+    return gs1, gs2, si1, si2

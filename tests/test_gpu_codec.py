@@ -98,3 +98,35 @@ def test_codec_file_matches_oracle_assembly_and_round_trips(tmp_path, oracle, us
             out1[perm_1[o1[3][0]]] = True
         assert np.array_equal(d1.reshape(-1)[~out1].view(np.uint32), enc1[~out1].view(np.uint32))
         assert np.all(np.abs(d1.reshape(-1)[out1] - enc1[out1]) <= 60 / 65535 + 1e-6)
+
+
+def test_empirical_dists_feed_the_codec(tmp_path):
+    """miracle.py:521-667 then compress/decompress: histograms from a few 'images', smoothed, used as the
+    arithmetic coder's model for a round trip."""
+    import compression_without_quantization_b200 as cwq
+    from compression_without_quantization_b200 import synthetic as syn
+    n1, n2 = int(np.prod(SHAPE1)), int(np.prod(SHAPE2))
+    p2 = syn.Normal(np.zeros(n2, np.float32), np.ones(n2, np.float32))
+
+    def images():
+        for k in range(3):
+            q1, q2 = syn.synthetic_posterior(n1, 80 + k), syn.synthetic_posterior(n2, 90 + k)
+            yield syn.Normal(q1[0], q1[1]), syn.Normal(q2[0], q2[1]), p2, _synthesis_2, SHAPE2
+    kw = dict(second_level_n_bits_per_group=10, second_level_max_group_size_bits=2, second_level_dim_kl_bit_limit=8,
+              first_level_n_bits_per_group=10, first_level_max_group_size_bits=4, first_level_dim_kl_bit_limit=8)
+    gs1, gs2, si1, si2 = cwq.build_empirical_dists(images(), 42, **kw)
+    assert gs1.size == 17 and gs2.size == 5 and si1.size == 1 + 2 ** 10
+    assert gs1[0] == 3 and gs2[0] == 3 and si1[0] == 3
+    assert gs1[1:].sum() == si1[1:].sum() and gs2[1:].sum() == si2[1:].sum()     # one index per group
+    assert (np.arange(17) * gs1).sum() == 3 * n1 and (np.arange(5) * gs2).sum() == 3 * n2
+    q1, q2 = syn.synthetic_posterior(n1, 80), syn.synthetic_posterior(n2, 90)
+    path = str(tmp_path / "e.miracle")
+    (s2, s1), _ = cwq.code_image_latents(syn.Normal(q1[0], q1[1]), syn.Normal(q2[0], q2[1]), p2, _synthesis_2, SHAPE1, SHAPE2, 42, 3, 6,
+                                         4, path, use_importance_sampling=True, second_level_group_dist_counts=gs2 + 1,
+                                         first_level_group_dist_counts=gs1 + 1, **kw)
+    d1, d2 = cwq.decode_image_latents(path, _synthesis_2, SHAPE1[3], SHAPE2[3], second_level_group_dist_counts=gs2 + 1,
+                                      first_level_group_dist_counts=gs1 + 1)
+    perm_1, perm_2 = cwq.latent_permutations(42, n1, n2)
+    enc1 = np.empty(n1, np.float32)
+    enc1[perm_1] = s1
+    assert np.mean(d1.reshape(-1) == enc1) > 0.99
