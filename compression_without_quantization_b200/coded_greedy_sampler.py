@@ -143,8 +143,8 @@ def decode_grouped_greedy_sample_batch(bitcodes, group_start_indices, proposals,
     sample = torch.empty(table.n, dtype=torch.float32, device=dev)
     E._lib.call("cwq_greedy_decode", E._ptr(groups.starts), E._ptr(groups.group_seed), E._ptr(groups.gid), E._ptr(indices),
                 table.n, n_steps, E.greedy_shard_scale(rho, n_steps), E._ptr(pl), E._ptr(ps), E._ptr(sample), E._stream())
-    host = sample.cpu().numpy()
-    return [host[table.starts[s]:table.starts[s] + sizes[s]].copy() for s in range(ns)]
+    host = E.to_host([sample])[0]
+    return [host[table.starts[s]:table.starts[s] + sizes[s]] for s in range(ns)]
 
 
 def decode_grouped_greedy_sample(sess, bitcode, group_start_indices, proposal, n_bits_per_step, n_steps, seed,

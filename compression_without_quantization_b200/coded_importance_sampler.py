@@ -242,8 +242,8 @@ def decode_grouped_importance_sample_batch(bitcodes, group_start_indices, propos
         pos_d = torch.from_numpy(pos).to(dev)
         q_d = torch.from_numpy(q.view(np.int16)).to(dev)
         E._lib.call("cwq_outlier_decode", E._ptr(sample), E._ptr(pos_d), E._ptr(q_d), int(pos.size), E._stream())
-    host = sample.cpu().numpy()
-    return [host[table.starts[s]:table.starts[s] + sizes[s]].copy() for s in range(ns)]
+    host = E.to_host([sample])[0]
+    return [host[table.starts[s]:table.starts[s] + sizes[s]] for s in range(ns)]
 
 
 def decode_grouped_importance_sample(sess, bitcode, group_start_indices, proposal, n_bits_per_group, seed,
