@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcwq.so")
+LIB_PATH = os.environ.get("CWQ_LIB") or os.path.join(_HERE, "libcwq.so")   # CWQ_LIB: A/B builds of the same ABI (tools/variants)
 
 ABI_VERSION = 1
 
