@@ -149,8 +149,9 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     per_step = []
     info = None
+    budget = float(os.environ.get("CWQ_BENCH_REFERENCE_SECONDS", "0")) or max(2.0, min(15.0, 120.0 / max(1, args.warmup + args.steps)))
     for i in range(args.warmup + args.steps):
-        info = cpu_reference_sample(segs, threads, target_seconds=max(2.0, min(15.0, 120.0 / (args.warmup + args.steps))))
+        info = cpu_reference_sample(segs, threads, target_seconds=budget)
         if i >= args.warmup:
             per_step.append(info)
     gps = float(np.mean([x["groups_per_s"] for x in per_step]))

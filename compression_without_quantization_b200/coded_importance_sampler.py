@@ -98,14 +98,13 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
     for t, p in zip(targets, proposals):
         _check_dtype(t, "Target")
         _check_dtype(p, "Proposal")
-    q_loc = [E.as_device_f32(t.loc, dev, "Target") for t in targets]
-    q_scale = [E.as_device_f32(t.scale, dev, "Target") for t in targets]
-    p_loc = [E.as_device_f32(p.loc, dev, "Proposal") for p in proposals]
-    p_scale = [E.as_device_f32(p.scale, dev, "Proposal") for p in proposals]
-    sizes = [int(x.numel()) for x in p_loc]
+    sizes = [int(np.prod(np.shape(p.loc))) if not hasattr(p.loc, "numel") else int(p.loc.numel()) for p in proposals]
     specs = [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
-    cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
-    job = E.ISJob(cat(q_loc), cat(q_scale), cat(p_loc), cat(p_scale), specs).prepare(sync=shard is not None)
+    q_loc = E.concat_to_device([t.loc for t in targets], dev, "Target")
+    q_scale = E.concat_to_device([t.scale for t in targets], dev, "Target")
+    p_loc = E.concat_to_device([p.loc for p in proposals], dev, "Proposal")
+    p_scale = E.concat_to_device([p.scale for p in proposals], dev, "Proposal")
+    job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs).prepare(sync=shard is not None)
     if stage == "groups":
         return job.sync_groups()
     if shard is None:

@@ -72,6 +72,29 @@ def as_device_f32(x, device=None, what="array"):
     return t.to(device, non_blocking=True).reshape(-1).contiguous()
 
 
+def concat_to_device(arrays, device=None, what="array"):
+    """Concatenation of flat float32 arrays on the device.  When the inputs are consecutive views of one host
+    buffer (a batch sliced into per-call pieces, as bench.py and pln-style callers produce) the whole span
+    goes over in ONE copy instead of one per piece."""
+    device = device or cuda_device()
+    if len(arrays) > 1 and all(isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.float32
+                               and a.is_contiguous() for a in arrays):
+        first = arrays[0]
+        pos = first.data_ptr()
+        adjacent = True
+        for a in arrays:
+            if a.data_ptr() != pos or a.untyped_storage().data_ptr() != first.untyped_storage().data_ptr():
+                adjacent = False
+                break
+            pos += a.numel() * 4
+        if adjacent:
+            total = sum(int(a.numel()) for a in arrays)
+            span = torch.as_strided(first.reshape(-1), (total,), (1,))
+            return span.to(device, non_blocking=True)
+    parts = [as_device_f32(a, device, what) for a in arrays]
+    return parts[0] if len(parts) == 1 else torch.cat(parts)
+
+
 def size_limit(max_group_size_bits, strict):
     """Running group size at which the reference's size test fires: CIS:185-187 evaluates
     ``np.log(size + 1) / np.log(2) > max_group_size_bits`` (CGS:230-232: ``>=``); the same expression is
