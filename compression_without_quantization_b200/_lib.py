@@ -50,7 +50,7 @@ SIGNATURES = {
     "cwq_expand_groups": (ctypes.c_int, [_P, _I64, _I64, _P, _I32, _P, _P, _P, _P]),
     "cwq_group_totals": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "cwq_is_encode_workspace_bytes": (_SZ, [_I64]),
-    "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _SZ, _P]),
+    "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _SZ, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "cwq_outlier_workspace_bytes": (_SZ, [_I64]),
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -87,6 +87,30 @@ __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, ui
   }
 }
 
+// 16 < G <= 64: coefficients and the per-(seed, q) Philox constants staged in this warp's shared slice
+__device__ __forceinline__ void is_score_range_mid(const float4* __restrict__ sc, const uint4* __restrict__ sq, int nq, uint32_t sseed,
+                                                   uint32_t kb, uint32_t ke, int lane, float& best, uint32_t& bestk) {
+  for (uint32_t k = kb + lane; k < ke; k += 32) {
+    const LaneShared ls = lane_shared(sseed, k);
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
+      float z[4];
+      const uint4 t = sq[q];
+      QuadConst qc;
+      qc.a = t.x; qc.b = t.y; qc.c3 = t.z;
+      normal_quad_tail(sseed, ls, qc, z);
+      float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
+      acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
+      acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
+      acc0 = __fmaf_rn(z[2], __fmaf_rn(c23.x, z[2], c23.y), acc0);
+      acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
+    }
+    float s = __fadd_rn(acc0, acc1);
+    if (s > best) { best = s; bestk = k; }
+  }
+}
+
 // any group size: coefficients read through the read-only path (warp-uniform addresses)
 __device__ __forceinline__ void is_score_range_generic(const float2* __restrict__ coef, int G, uint32_t sseed, uint32_t kb,
                                                        uint32_t ke, int lane, float& best, uint32_t& bestk) {
@@ -110,12 +134,16 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
   }
 }
 
+// SMALL: every group has <= 16 dims (the reference defaults): only the register-resident path is compiled in,
+// which keeps the kernel at 64 registers / 4 resident CTAs per SM (measured best).
+template <bool SMALL>
 __global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
                                                          long long g0, long long ng, const long long* __restrict__ ng_dev,
                                                          const ull* __restrict__ unit_off,
                                                          ull* __restrict__ counter, ull* __restrict__ keys) {
-  __shared__ float4 s_coef[IS_WARPS][8];
+  __shared__ float4 s_coef[IS_WARPS][SMALL ? 8 : 32];   // 16 or 64 (a, b) pairs per warp
+  __shared__ uint4 s_quad[IS_WARPS][SMALL ? 1 : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (ng_dev) ng = *ng_dev;
   const ull n_units = unit_off[ng];
@@ -145,7 +173,7 @@ __global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restric
       const uint32_t sseed = gseed[g];
       float best = __uint_as_float(0xff800000u);
       uint32_t bestk = 0xffffffffu;
-      if (G <= 16) {
+      if (SMALL || G <= 16) {
         __syncwarp();
         if (lane < 16) my_coef[lane] = lane < G ? coef[s + lane] : make_float2(0.0f, 0.0f);
         __syncwarp();
@@ -157,7 +185,18 @@ __global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restric
           case 3: is_score_range<3>(sc, sseed, kb, ke, lane, best, bestk); break;
           default: is_score_range<4>(sc, sseed, kb, ke, lane, best, bestk); break;
         }
-      } else {
+      } else if (!SMALL && G <= 64) {
+        const int nq = (G + 3) >> 2;
+        __syncwarp();
+        my_coef[lane] = lane < G ? coef[s + lane] : make_float2(0.0f, 0.0f);
+        my_coef[lane + 32] = lane + 32 < G ? coef[s + lane + 32] : make_float2(0.0f, 0.0f);
+        if (lane < nq) {
+          QuadConst c = quad_const(sseed, (uint32_t)lane);
+          s_quad[warp][lane] = make_uint4(c.a, c.b, c.c3, 0u);
+        }
+        __syncwarp();
+        is_score_range_mid(s_coef[warp], s_quad[warp], nq, sseed, kb, ke, lane, best, bestk);
+      } else if (!SMALL) {
         is_score_range_generic(coef + s, G, sseed, kb, ke, lane, best, bestk);
       }
       ull key = bestk == 0xffffffffu ? 0ull : pack_key(best, bestk);
@@ -599,15 +638,17 @@ static cudaEvent_t g_ev0[PROFILE_RING], g_ev1[PROFILE_RING];
 static int g_profile_count = 0;
 static bool g_profile_events_ready = false;
 
-static int g_sm_count = 0, g_is_blocks_per_sm = 0;
+static int g_sm_count = 0, g_is_blocks_per_sm = 0, g_is_blocks_per_sm_any = 0;
 static int ensure_device_props() {
   if (g_sm_count > 0) return CWQ_OK;
   int dev = 0;
   CWQ_CUDA(cudaGetDevice(&dev));
   int sms = 0, bps = 0;
   CWQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score, IS_THREADS, 0));
+  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<true>, IS_THREADS, 0));
   g_is_blocks_per_sm = bps > 0 ? bps : 1;
+  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<false>, IS_THREADS, 0));
+  g_is_blocks_per_sm_any = bps > 0 ? bps : 1;
   if (const char* e = getenv("CWQ_IS_BLOCKS_PER_SM")) {   // tuning knob: fewer resident CTAs than the occupancy limit
     int v = atoi(e);
     if (v >= 1 && v <= g_is_blocks_per_sm) g_is_blocks_per_sm = v;
@@ -660,8 +701,9 @@ extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
 }
 
 extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
-                             int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, uint32_t* index,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, int64_t max_group_size,
+                             uint32_t* index, void* workspace, size_t workspace_bytes, void* stream) {
+  CWQ_REQUIRE(max_group_size >= 0, "max_group_size must be an upper bound of the group sizes");
   CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
   CWQ_REQUIRE(!n_groups_dev || (g0 == 0 && g1 == n_groups), "a device-side group count needs the full range [0, capacity)");
   if (g0 == g1) return CWQ_OK;
@@ -684,8 +726,12 @@ extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int
   CWQ_LAUNCH_CHECK();
   const bool prof = g_profile && g_profile_count < PROFILE_RING;
   if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
-  k_is_score<<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K, group_seed,
-                                                                     g0, ng, ngd, unit_off, counter, keys);
+  if (max_group_size <= 16)
+    k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
+                                                                              group_seed, g0, ng, ngd, unit_off, counter, keys);
+  else
+    k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
+                                                                                   group_seed, g0, ng, ngd, unit_off, counter, keys);
   CWQ_LAUNCH_CHECK();
   if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
   k_is_index<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(keys, g0, g1, ngd, index);

@@ -313,8 +313,12 @@ class ISJob:
         g1 = cap if g1 is None else g1
         wsb = _lib.load().cwq_is_encode_workspace_bytes(cap)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        if self.forced_starts is None:
+            max_size = max(self.table.max_size_limit, 1)
+        else:
+            max_size = max(int(np.diff(np.asarray(st)).max()) for st in self.forced_starts)
         _lib.call("cwq_is_encode", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
-                  cap, self._ng_dev(), g0, g1, _ptr(self.index), _ptr(ws), wsb, _stream())
+                  cap, self._ng_dev(), g0, g1, max_size, _ptr(self.index), _ptr(ws), wsb, _stream())
         return self
 
     def decode(self):

@@ -103,11 +103,12 @@ CWQ_API int cwq_group_totals(const float* kl, const int64_t* starts, int64_t n_g
 
 /* ---- importance sampler ----------------------------------------------------------------------
  * CIS:55-63 for groups [g0, g1): index[g] = first candidate maximising the importance weight
- * (0-based; the reference codes index + 1). */
+ * (0-based; the reference codes index + 1).  max_group_size: an upper bound of the group sizes (the largest
+ * size_limit of the segments); <= 16 selects the kernel specialised for the reference defaults. */
 CWQ_API size_t cwq_is_encode_workspace_bytes(int64_t n_groups);
 CWQ_API int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
-                  int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, uint32_t* index,
-                  void* workspace, size_t workspace_bytes, void* stream);
+                  int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, int64_t max_group_size,
+                  uint32_t* index, void* workspace, size_t workspace_bytes, void* stream);
 /* CIS:104-109 + CIS:265/347: regenerate row index[g] of every group and un-rescale:
  * sample[i] = p_scale[i] * z + p_loc[i]. */
 CWQ_API int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,

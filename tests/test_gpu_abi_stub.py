@@ -46,7 +46,7 @@ def test_integration_md_stub_runs_and_matches_package():
     lib.cwq_is_encode_workspace_bytes.restype = SZ
     wsb = lib.cwq_is_encode_workspace_bytes(I64(ng))
     ws2 = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    assert lib.cwq_is_encode(ptr(coef), ptr(starts), ptr(K), ptr(gseed), I64(ng), None, I64(0), I64(ng), ptr(index), ptr(ws2),
+    assert lib.cwq_is_encode(ptr(coef), ptr(starts), ptr(K), ptr(gseed), I64(ng), None, I64(0), I64(ng), I64(16), ptr(index), ptr(ws2),
                              SZ(wsb), st) == 0
     sample = torch.empty(n, device="cuda")
     assert lib.cwq_is_decode(ptr(starts), ptr(gseed), ptr(gid), ptr(index), I64(n), ptr(p_loc), ptr(p_scale), ptr(sample), st) == 0
@@ -60,7 +60,7 @@ def test_integration_md_stub_runs_and_matches_package():
     inl[want[3][0]] = False
     assert np.array_equal(sample.cpu().numpy()[inl].view(np.uint32), want[0][inl].view(np.uint32))
     # a wrong argument is reported, not ignored
-    assert lib.cwq_is_encode(ptr(coef), ptr(starts), ptr(K), ptr(gseed), I64(ng), None, I64(5), I64(2), ptr(index), ptr(ws2),
+    assert lib.cwq_is_encode(ptr(coef), ptr(starts), ptr(K), ptr(gseed), I64(ng), None, I64(5), I64(2), I64(16), ptr(index), ptr(ws2),
                              SZ(wsb), st) != 0
     lib.cwq_last_error.restype = ctypes.c_char_p
     assert b"bad group range" in lib.cwq_last_error()

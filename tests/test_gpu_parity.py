@@ -460,3 +460,19 @@ def test_greedy_kernel_variants_agree(cwq, syn):
     idx = job.indices.cpu().numpy().reshape(ng, 5)
     assert np.array_equal(idx[ng // 3:2 * ng // 3], outs[0][0].reshape(ng, 5)[ng // 3:2 * ng // 3])
     assert not idx[:ng // 3].any() and not idx[2 * ng // 3:].any()
+
+
+@pytest.mark.parametrize("m,n", [(5, 900), (6, 1500), (7, 1200)])
+def test_is_large_groups_bit_exact_with_injected_draws(cwq, oracle, syn, m, n):
+    """max_group_size_bits above the reference default: groups of up to 32 / 64 dims take the shared-memory
+    staged path, up to 128 the generic path; all must agree with the oracle bit for bit."""
+    rng = np.random.default_rng(m)
+    q_loc = (0.25 * rng.normal(size=n) * (rng.random(n) < 0.3)).astype(np.float32)     # low KL per dim -> large groups
+    q_scale = np.exp(-np.abs(rng.normal(0, 0.12, n))).astype(np.float32)
+    p = syn.Normal(np.zeros(n, np.float32), np.ones(n, np.float32))
+    got = cwq.code_grouped_importance_sample(None, syn.Normal(q_loc, q_scale), p, 11, 11, m, 9)
+    want = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p.loc, p.scale), 11, 11, m, 9,
+                                                 normal_source=_src(cwq))
+    assert np.diff(got[2]).max() > 16
+    assert np.array_equal(got[2], want[2]) and got[1] == want[1]
+    assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32))

@@ -83,6 +83,12 @@ def main():
             arrays = [synthetic_posterior(1 << 20, 77)]
             specs = [E.SegmentSpec(1 << 20, 42, bits, 4, bits - 2, True)]
             is_config("configs[2]: 1M dims, IS {} bits".format(bits), arrays, specs, args.reps)
+    if want("big"):   # non-default group sizes: 32- and 64-dim groups (shared-memory staged path) and 128 (generic path)
+        for m in (5, 6, 7):
+            arrays = [synthetic_posterior(1 << 20, 78)]
+            arrays = [(a[0] * 0.3, np.exp(-np.abs(np.log(a[1])) * 0.2).astype(np.float32), a[2], a[3]) for a in arrays]
+            specs = [E.SegmentSpec(1 << 20, 42, 20, m, 16, True)]
+            is_config("1M low-KL dims, IS 20 bits, max_group_size_bits {}".format(m), arrays, specs, args.reps)
     if want("c0"):
         arrays = [synthetic_posterior(n1, 0)]
         specs = [E.SegmentSpec(n1, 42, 30 * 14, 12, float("inf"), False)]
