@@ -157,26 +157,33 @@ __global__ void __launch_bounds__(128) k_tile_entries(const int* __restrict__ en
   }
 }
 
-// one CTA per tile: the tile's next[] slice is staged in shared memory (coalesced), then one thread
-// follows the chain through it (dependent shared loads instead of dependent global loads)
+// one CTA per tile: the tile's next[] slice is staged in shared memory (coalesced), one thread follows the
+// chain through it setting flags in shared memory, then the whole tile's flags are written out coalesced
+// (every byte of mark[] is written here, so no memset is needed)
 __global__ void __launch_bounds__(256) k_mark(const int* __restrict__ entry1, const int* __restrict__ next, long long n,
                                               long long n_tiles, uint8_t* __restrict__ mark) {
   __shared__ int snext[TILE1];
+  __shared__ uint8_t sflag[TILE1];
   const long long t = blockIdx.x;
   if (t >= n_tiles) return;
   const long long v0 = entry1[t];
-  if (v0 < 0) return;
   const long long tile0 = t * TILE1;
   const long long t_end = tile0 + TILE1 < n ? tile0 + TILE1 : n;
-  for (int j = threadIdx.x; j < TILE1; j += blockDim.x) snext[j] = (tile0 + j < n) ? next[tile0 + j] : (int)n;
+  for (int j = threadIdx.x; j < TILE1; j += blockDim.x) {
+    sflag[j] = 0;
+    if (v0 >= 0) snext[j] = (tile0 + j < n) ? next[tile0 + j] : (int)n;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && v0 >= 0) {
     long long v = v0;
     while (v < t_end) {
-      mark[v] |= 1;
+      sflag[v - tile0] = 1;
       v = snext[v - tile0];
     }
   }
+  __syncthreads();
+  for (int j = threadIdx.x; j < TILE1; j += blockDim.x)
+    if (tile0 + j < n) mark[tile0 + j] = sflag[j];
 }
 
 __global__ void k_mark_segment_starts(const cwq_segment* __restrict__ segs, int n_seg, uint8_t* __restrict__ mark) {
@@ -333,7 +340,6 @@ extern "C" int cwq_group(const float* kl, int64_t n, const cwq_segment* segments
     set_error("cwq_group: workspace too small");
     return CWQ_ERR_WORKSPACE;
   }
-  CWQ_CUDA(cudaMemsetAsync(mark, 0, (size_t)n, st));
   CWQ_CUDA(cudaMemsetAsync(entry1, 0xff, (size_t)n_tiles * 4, st));
   CWQ_CUDA(cudaMemsetAsync(entry2, 0xff, (size_t)n_super * 4, st));
   k_next<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(kl, n, segments, n_segments, next, first);
