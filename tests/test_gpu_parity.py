@@ -476,3 +476,60 @@ def test_is_large_groups_bit_exact_with_injected_draws(cwq, oracle, syn, m, n):
     assert np.diff(got[2]).max() > 16
     assert np.array_equal(got[2], want[2]) and got[1] == want[1]
     assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised sweep: many small problems, every parameter drawn at random
+# ------------------------------------------------------------------------------------------------
+def test_randomised_importance_sampler_sweep(cwq, oracle, syn):
+    rng = np.random.default_rng(20261018)
+    for case in range(40):
+        n = int(rng.integers(1, 260))
+        bits = int(rng.integers(4, 13))
+        m = int(rng.integers(0, 6))
+        limit = float(rng.choice([2.0, 5.0, bits - 2.0, bits + 3.0]))
+        seed = int(rng.choice([0, 1, 42, 2 ** 31 - 1, 2 ** 32 - 3, int(rng.integers(0, 2 ** 32))]))
+        q_scale = np.exp(rng.normal(-0.4, 0.8, n)).astype(np.float32)          # some posteriors wider than the prior
+        q_loc = (rng.normal(0, 1.5, n) * (rng.random(n) < 0.5)).astype(np.float32)
+        p_loc = rng.normal(size=n).astype(np.float32) if case % 2 else np.zeros(n, np.float32)
+        p_scale = np.exp(rng.normal(0, 0.5, n)).astype(np.float32) if case % 2 else np.ones(n, np.float32)
+        q_loc = (p_loc + p_scale * q_loc).astype(np.float32)
+        q_scale = (p_scale * q_scale).astype(np.float32)
+        got = cwq.code_grouped_importance_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), seed, bits, m, limit)
+        want = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), seed, bits, m,
+                                                     limit, normal_source=_src(cwq))
+        ctx = (case, n, bits, m, limit, seed)
+        assert np.array_equal(got[2], want[2]), ctx
+        assert got[1] == want[1], ctx
+        assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32)), ctx
+        assert np.array_equal(got[3][0], want[3][0]) and np.array_equal(got[3][1], want[3][1]), ctx
+        dec = cwq.decode_grouped_importance_sample(None, got[1], [int(x) for x in got[2][:-1]], syn.Normal(p_loc, p_scale), bits, seed,
+                                                   got[3][0], got[3][1])
+        inl = np.ones(n, bool)
+        inl[got[3][0]] = False
+        assert np.array_equal(dec[inl].view(np.uint32), got[0][inl].view(np.uint32)), ctx
+
+
+def test_randomised_greedy_sweep(cwq, oracle, syn):
+    rng = np.random.default_rng(7)
+    for case in range(16):
+        n = int(rng.integers(1, 200))
+        steps = int(rng.integers(1, 5))
+        b = int(rng.integers(1, 9))
+        m = int(rng.integers(0, 7))
+        seed = int(rng.choice([0, 42, 4294967, 2 ** 32 - 1, int(rng.integers(0, 2 ** 32))]))
+        rho = float(rng.choice([1.0, 0.7, 1.3]))
+        q_scale = np.exp(rng.normal(-0.5, 0.6, n)).astype(np.float32)
+        q_loc = rng.normal(0, 1.0, n).astype(np.float32)
+        p_loc = rng.normal(size=n).astype(np.float32) if case % 2 else np.zeros(n, np.float32)
+        p_scale = np.exp(rng.normal(0, 0.4, n)).astype(np.float32)
+        q_loc = (p_loc + p_scale * q_loc).astype(np.float32)
+        q_scale = (p_scale * q_scale).astype(np.float32)
+        got = cwq.code_grouped_greedy_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), steps, b, seed, m, rho=rho)
+        want = oracle.code_grouped_greedy_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), steps, b, seed, m,
+                                                 rho=rho, normal_source=_src(cwq))
+        ctx = (case, n, steps, b, m, seed, rho)
+        assert got[2] == want[2] and got[1] == want[1], ctx
+        assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32)), ctx
+        dec = cwq.decode_grouped_greedy_sample(None, got[1], list(got[2][:-1]), syn.Normal(p_loc, p_scale), b, steps, seed, rho=rho)
+        assert np.array_equal(dec.view(np.uint32), got[0].view(np.uint32)), ctx
