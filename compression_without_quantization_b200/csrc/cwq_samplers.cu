@@ -137,7 +137,7 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 // SMALL: every group has <= 16 dims (the reference defaults): only the register-resident path is compiled in,
 // which keeps the kernel at 64 registers / 4 resident CTAs per SM (measured best).
 template <bool SMALL>
-__global__ void __launch_bounds__(IS_THREADS) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
+__global__ void __launch_bounds__(IS_THREADS, SMALL ? 4 : 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
                                                          long long g0, long long ng, const long long* __restrict__ ng_dev,
                                                          const ull* __restrict__ unit_off,

@@ -96,10 +96,25 @@ __device__ __forceinline__ void stream_block_tail(uint32_t sseed, const LaneShar
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// Bits of 1.0f, read from constant memory so that ptxas keeps them in a REGISTER: LOP3 has one immediate
+// slot, so `(x & 0x7fffff) | 0x3f800000` with two literals costs two LOP3 per Philox word; with the
+// exponent in a register it is one (`lop3 d, x, 0x7fffff, one, (a&b)|c`).  Same bits either way.
+static __constant__ uint32_t c_one_bits = 0x3f800000u;
+
+__device__ __forceinline__ float mantissa_to_1_2(uint32_t x) {
+#ifdef CWQ_TWO_LOP_MASK
+  return __uint_as_float((x & 0x007fffffu) | 0x3f800000u);
+#else
+  uint32_t r;
+  asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(r) : "r"(x), "r"(c_one_bits));
+  return __uint_as_float(r);
+#endif
+}
+
 // Two N(0,1) values from two Philox words (Box-Muller, 23-bit uniforms).
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, float& zo) {
-  float f1 = __uint_as_float((xa & 0x007fffffu) | 0x3f800000u);  // [1,2)
-  float f2 = __uint_as_float((xb & 0x007fffffu) | 0x3f800000u);
+  float f1 = mantissa_to_1_2(xa);  // [1,2)
+  float f2 = mantissa_to_1_2(xb);
   float u1 = __fsub_rn(2.0f, f1);                                // (0,1], exact
   float th = __fmaf_rn(f2, 6.2831855f, -9.424778f);              // [-pi, pi)
   float l, r, c, s;
