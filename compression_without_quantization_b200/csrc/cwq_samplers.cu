@@ -60,52 +60,46 @@ __device__ __forceinline__ ull warp_max_key(ull key) {
   return key;
 }
 
-// candidates [kb, ke) of one group, NQ quads of coefficients staged in this warp's shared slice.
-// Per candidate: 2 shared IMAD.WIDE (lane_shared) + 14 per quad (rounds 3..9); the (seed, q) parts of
-// rounds 1-2 live in registers (qc).
+// score of one quad: two accumulators (even / odd dims), spec section 3.7
+__device__ __forceinline__ void is_score_quad(const float4* __restrict__ sc, int q, const float (&z)[4], float& acc0, float& acc1) {
+  const float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
+  acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
+  acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
+  acc0 = __fmaf_rn(z[2], __fmaf_rn(c23.x, z[2], c23.y), acc0);
+  acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
+}
+
+// candidates [kb, ke) of one group of NQ <= 4 quads (one unit), coefficients staged in this warp's shared slice.
+// Per candidate: 2 shared IMAD.WIDE (lane_shared) + 14 per block (rounds 3..9), min(NQ, 3) blocks; the
+// (seed, block) parts of rounds 0-2 live in registers (bc).
 template <int NQ>
 __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
                                                int lane, float& best, uint32_t& bestk) {
-  QuadConst qc[NQ > 0 ? NQ : 1];
+  constexpr int NB = NQ < 3 ? NQ : 3;
+  BlockConst bc[NB > 0 ? NB : 1];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) qc[q] = quad_const(sseed, (uint32_t)q);
+  for (int j = 0; j < NB; ++j) bc[j] = block_const(sseed, (uint32_t)j);
   for (uint32_t k = kb + lane; k < ke; k += 32) {
-    const LaneShared ls = lane_shared(sseed, k);
     float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      float z[4];
-      normal_quad_tail(sseed, ls, qc[q], z);
-      float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
-      acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
-      acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
-      acc0 = __fmaf_rn(z[2], __fmaf_rn(c23.x, z[2], c23.y), acc0);
-      acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
+    if (NQ > 0) {
+      const LaneShared ls = lane_shared(sseed, k);
+      unit_quads<(NQ > 0 ? NQ : 1)>(ls, [&](int b) { return bc[b]; },
+                                    [&](int q, const float (&z)[4]) { is_score_quad(sc, q, z, acc0, acc1); });
     }
     float s = __fadd_rn(acc0, acc1);
     if (s > best) { best = s; bestk = k; }
   }
 }
 
-// 16 < G <= 64: coefficients and the per-(seed, q) Philox constants staged in this warp's shared slice
-__device__ __forceinline__ void is_score_range_mid(const float4* __restrict__ sc, const uint4* __restrict__ sq, int nq, uint32_t sseed,
+// 16 < G <= 64: coefficients and the per-(seed, block) Philox constants staged in this warp's shared slice
+__device__ __forceinline__ void is_score_range_mid(const float4* __restrict__ sc, const uint4* __restrict__ sb, int nq, uint32_t sseed,
                                                    uint32_t kb, uint32_t ke, int lane, float& best, uint32_t& bestk) {
   for (uint32_t k = kb + lane; k < ke; k += 32) {
     const LaneShared ls = lane_shared(sseed, k);
     float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 2
-    for (int q = 0; q < nq; ++q) {
-      float z[4];
-      const uint4 t = sq[q];
-      QuadConst qc;
-      qc.a = t.x; qc.b = t.y; qc.c3 = t.z;
-      normal_quad_tail(sseed, ls, qc, z);
-      float4 c01 = sc[2 * q], c23 = sc[2 * q + 1];
-      acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
-      acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
-      acc0 = __fmaf_rn(z[2], __fmaf_rn(c23.x, z[2], c23.y), acc0);
-      acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
-    }
+    row_quads(ls, nq,
+              [&](int j) { const uint4 t = sb[j]; BlockConst c; c.a = t.x; c.b = t.y; c.c3 = t.z; return c; },
+              [&](int q, const float (&z)[4]) { is_score_quad(sc, q, z, acc0, acc1); });
     float s = __fadd_rn(acc0, acc1);
     if (s > best) { best = s; bestk = k; }
   }
@@ -118,17 +112,16 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
   for (uint32_t k = kb + lane; k < ke; k += 32) {
     const LaneShared ls = lane_shared(sseed, k);
     float acc0 = 0.0f, acc1 = 0.0f;
-    for (int q = 0; q < nq; ++q) {
-      float z[4];
-      normal_quad_tail(sseed, ls, quad_const(sseed, (uint32_t)q), z);
+    row_quads(ls, nq, [&](int j) { return block_const(sseed, (uint32_t)j); },
+              [&](int q, const float (&z)[4]) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int d = 4 * q + j;
-        float2 c = d < G ? __ldg(&coef[d]) : make_float2(0.0f, 0.0f);
-        float w = __fmaf_rn(c.x, z[j], c.y);
-        if (j & 1) acc1 = __fmaf_rn(z[j], w, acc1); else acc0 = __fmaf_rn(z[j], w, acc0);
-      }
-    }
+                for (int jj = 0; jj < 4; ++jj) {
+                  int d = 4 * q + jj;
+                  float2 c = d < G ? __ldg(&coef[d]) : make_float2(0.0f, 0.0f);
+                  float w = __fmaf_rn(c.x, z[jj], c.y);
+                  if (jj & 1) acc1 = __fmaf_rn(z[jj], w, acc1); else acc0 = __fmaf_rn(z[jj], w, acc0);
+                }
+              });
     float s = __fadd_rn(acc0, acc1);
     if (s > best) { best = s; bestk = k; }
   }
@@ -190,8 +183,8 @@ __global__ void __launch_bounds__(IS_THREADS, SMALL ? 4 : 3) k_is_score(const fl
         __syncwarp();
         my_coef[lane] = lane < G ? coef[s + lane] : make_float2(0.0f, 0.0f);
         my_coef[lane + 32] = lane + 32 < G ? coef[s + lane + 32] : make_float2(0.0f, 0.0f);
-        if (lane < nq) {
-          QuadConst c = quad_const(sseed, (uint32_t)lane);
+        if (lane < row_blocks(nq)) {
+          BlockConst c = block_const(sseed, (uint32_t)lane);
           s_quad[warp][lane] = make_uint4(c.a, c.b, c.c3, 0u);
         }
         __syncwarp();
@@ -281,6 +274,20 @@ __global__ void __launch_bounds__(256) k_outlier_decode(float* __restrict__ samp
 // ------------------------------------------------------------------------------------------
 constexpr int GREEDY_THREADS = 512;
 
+// one quad of the greedy score: u = z * c + e, acc += u * u (even / odd dims), spec section 3.8
+__device__ __forceinline__ void greedy_score_quad(const float4* __restrict__ ce4, int q, const float (&z)[4], float& acc0, float& acc1) {
+  const float4 c01 = ce4[2 * q], c23 = ce4[2 * q + 1];
+  float u0 = __fmaf_rn(z[0], c01.x, c01.y);
+  float u1 = __fmaf_rn(z[1], c01.z, c01.w);
+  float u2 = __fmaf_rn(z[2], c23.x, c23.y);
+  float u3 = __fmaf_rn(z[3], c23.z, c23.w);
+  acc0 = __fmaf_rn(u0, u0, acc0);
+  acc1 = __fmaf_rn(u1, u1, acc1);
+  acc0 = __fmaf_rn(u2, u2, acc0);
+  acc1 = __fmaf_rn(u3, u3, acc1);
+}
+
+
 __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* __restrict__ tparam, const long long* __restrict__ starts,
                                                                   const uint32_t* __restrict__ gseed, long long g0, int n_steps,
                                                                   uint32_t n_samples, float shard_scale,
@@ -308,9 +315,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
       float2 t = tparam[s + d];
       ce[d].y = __fmul_rn(__fsub_rn(best[d], t.x), t.y);
     }
-    for (int q = tid; q < nq; q += GREEDY_THREADS) {
-      QuadConst c = quad_const(sseed, (uint32_t)q);
-      qtab[q] = make_uint4(c.a, c.b, c.c3, 0u);
+    for (int j = tid; j < row_blocks(nq); j += GREEDY_THREADS) {
+      BlockConst c = block_const(sseed, (uint32_t)j);
+      qtab[j] = make_uint4(c.a, c.b, c.c3, 0u);
     }
     __syncthreads();
     float bs = __uint_as_float(0x7f800000u);
@@ -319,23 +326,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
     for (uint32_t k = tid; k < n_samples; k += GREEDY_THREADS) {
       const LaneShared ls = lane_shared(sseed, k);
       float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 2
-      for (int q = 0; q < nq; ++q) {
-        float z[4];
-        const uint4 t = qtab[q];
-        QuadConst qc;
-        qc.a = t.x; qc.b = t.y; qc.c3 = t.z;
-        normal_quad_tail(sseed, ls, qc, z);
-        float4 c01 = ce4[2 * q], c23 = ce4[2 * q + 1];
-        float u0 = __fmaf_rn(z[0], c01.x, c01.y);
-        float u1 = __fmaf_rn(z[1], c01.z, c01.w);
-        float u2 = __fmaf_rn(z[2], c23.x, c23.y);
-        float u3 = __fmaf_rn(z[3], c23.z, c23.w);
-        acc0 = __fmaf_rn(u0, u0, acc0);
-        acc1 = __fmaf_rn(u1, u1, acc1);
-        acc0 = __fmaf_rn(u2, u2, acc0);
-        acc1 = __fmaf_rn(u3, u3, acc1);
-      }
+      row_quads(ls, nq,
+                [&](int j) { const uint4 t = qtab[j]; BlockConst c; c.a = t.x; c.b = t.y; c.c3 = t.z; return c; },
+                [&](int q, const float (&z)[4]) { greedy_score_quad(ce4, q, z, acc0, acc1); });
       float sc = __fadd_rn(acc0, acc1);
       if (sc < bs) { bs = sc; bk = k; }
     }
@@ -417,9 +410,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
       uint4* s_q = reinterpret_cast<uint4*>(smem_raw + (size_t)Gp * sizeof(float2));
       const uint32_t sseed = 1000u * gseed[g] + (uint32_t)step;
       for (int d = tid; d < Gp; d += GREEDY_THREADS) s_ce[d] = d < G ? ce[s + d] : make_float2(0.0f, 0.0f);
-      for (int q = tid; q < nq; q += GREEDY_THREADS) {
-        QuadConst c = quad_const(sseed, (uint32_t)q);
-        s_q[q] = make_uint4(c.a, c.b, c.c3, 0u);
+      for (int jb = tid; jb < row_blocks(nq); jb += GREEDY_THREADS) {
+        BlockConst c = block_const(sseed, (uint32_t)jb);
+        s_q[jb] = make_uint4(c.a, c.b, c.c3, 0u);
       }
       __syncthreads();
       float bs = __uint_as_float(0x7f800000u);
@@ -429,23 +422,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
       for (uint32_t k = chunk * GREEDY_CHUNK + tid; k < k_end; k += GREEDY_THREADS) {
         const LaneShared ls = lane_shared(sseed, k);
         float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 2
-        for (int q = 0; q < nq; ++q) {
-          float z[4];
-          const uint4 t = s_q[q];
-          QuadConst qc;
-          qc.a = t.x; qc.b = t.y; qc.c3 = t.z;
-          normal_quad_tail(sseed, ls, qc, z);
-          float4 c01 = ce4[2 * q], c23 = ce4[2 * q + 1];
-          float u0 = __fmaf_rn(z[0], c01.x, c01.y);
-          float u1 = __fmaf_rn(z[1], c01.z, c01.w);
-          float u2 = __fmaf_rn(z[2], c23.x, c23.y);
-          float u3 = __fmaf_rn(z[3], c23.z, c23.w);
-          acc0 = __fmaf_rn(u0, u0, acc0);
-          acc1 = __fmaf_rn(u1, u1, acc1);
-          acc0 = __fmaf_rn(u2, u2, acc0);
-          acc1 = __fmaf_rn(u3, u3, acc1);
-        }
+        row_quads(ls, nq,
+                  [&](int jb) { const uint4 t = s_q[jb]; BlockConst c; c.a = t.x; c.b = t.y; c.c3 = t.z; return c; },
+                  [&](int q, const float (&z)[4]) { greedy_score_quad(ce4, q, z, acc0, acc1); });
         float sc = __fadd_rn(acc0, acc1);
         if (sc < bs) { bs = sc; bk = k; }
       }

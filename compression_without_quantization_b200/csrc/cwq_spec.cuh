@@ -45,56 +45,80 @@ __device__ __forceinline__ void mulwide(uint32_t a, uint32_t m, uint32_t& hi, ui
   asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(m));
 }
 
-// The candidate stream's block: counter (0, k, 0, q), key (stream_seed, 42).
-// Why this placement: with c0 = c2 = 0 round 0 needs no multiply, and in rounds 1-2 one product of each
-// pair depends only on (q, seed) -- hoisted out of the candidate loop -- while the other depends only on
-// (k, seed) and is shared by all quads of a candidate.  Only rounds 3..9 cost two IMAD.WIDE per block:
-// 14.5 instead of 20 wide multiplies per block.  IMAD.WIDE (4.25 cycles per warp on the FMA pipe, which
-// FP32 work shares) is the binding resource of the whole path (profiles/r01_pipe_overlap_microbench.log).
-__device__ __forceinline__ void stream_block(uint32_t sseed, uint32_t k, uint32_t q, uint32_t (&o)[4]) {
-  philox4x32_10(0u, k, 0u, q, sseed, STREAM_KEY1, o);
+// ------------------------------------------------------------------------------------------------
+// The candidate stream, replacing tf.random.stateless_normal (misc.py:10-11).
+//
+//   block(s, k, j) = Philox4x32-10(counter = (s, k, 0, j), key = (STREAM_KEY0, 42))
+//
+// s = stream seed (exactly what the reference passes as `seed`), k = candidate (row), j = block in the row.
+// A row is cut into UNITS of 16 dims.  Unit u owns blocks 3u, 3u+1, 3u+2 and turns their 384 bits into
+// sixteen 23-bit uniforms: quad b < 3 of the unit takes the low 23 bits of the four words of block 3u+b;
+// quad 3 takes, for word i, the TOP BYTES of word i of the three blocks (block 3u in bits 0-7, 3u+1 in
+// bits 8-15, 3u+2 in bits 16-22).  Low 23 bits and top byte of a word do not overlap, so the sixteen
+// uniforms are independent.  Within a quad, words (0,1) -> dims 4q, 4q+1 and (2,3) -> dims 4q+2, 4q+3.
+//
+// Why this shape: IMAD.WIDE (4 cycles per warp on the FMA-heavy pipe) is the scarcest resource of the
+// scoring loop.  (1) 3 instead of 4 Philox blocks per 16 dims.  (2) With c2 = 0, round 0 needs one
+// multiply that depends on s only; in rounds 1-2 one product of each pair depends on (s, j) only --
+// hoisted out of the candidate loop -- and the other on (s, k) only -- shared by all blocks of a candidate.
+// Only rounds 3..9 cost two IMAD.WIDE per block.  (3) The key is a constant, so the round keys are
+// immediates of the three-input XORs instead of per-group registers.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t STREAM_KEY0 = 0x6A09E667u;     // frac(sqrt 2): a nothing-up-my-sleeve constant
+
+__device__ __forceinline__ void stream_block(uint32_t sseed, uint32_t k, uint32_t j, uint32_t (&o)[4]) {
+  philox4x32_10(sseed, k, 0u, j, STREAM_KEY0, STREAM_KEY1, o);
 }
 
+// number of Philox blocks a row of nq quads (4 dims each) needs: 3 per full unit, min(rest, 3) for the tail
+__host__ __device__ __forceinline__ int row_blocks(int nq) { return 3 * (nq >> 2) + ((nq & 3) < 3 ? (nq & 3) : 3); }
+
 // -- the same block, factored for the hot loops --------------------------------------------------
-// state after round 2 is (h ^ a, l, l0 ^ b, c3) with (a, b, c3) a function of (seed, q) only and
-// (h, l, l0) a function of (seed, k) only.
-struct QuadConst { uint32_t a, b, c3; };
+// state after round 2 is (h ^ a, l, l0 ^ b, c3) with (a, b, c3) a function of (s, j) only and
+// (h, l, l0) a function of (s, k) only.
+struct BlockConst { uint32_t a, b, c3; };
 struct LaneShared { uint32_t h, l, l0; };
 
-__device__ __forceinline__ QuadConst quad_const(uint32_t sseed, uint32_t q) {
-  uint32_t h1, l1, h0, l0;
-  mulwide_generic(q ^ STREAM_KEY1, PHILOX_M1, h1, l1);               // round 1, p1 (constant when q is)
-  mulwide(h1 ^ (sseed + PHILOX_W0), PHILOX_M0, h0, l0);              // round 2, p0
-  QuadConst c;
-  c.a = l1 ^ (sseed + 2u * PHILOX_W0);
+__device__ __forceinline__ BlockConst block_const(uint32_t sseed, uint32_t j) {
+  uint32_t hs, ls, h1, l1, h0, l0;
+  mulwide(sseed, PHILOX_M0, hs, ls);                                        // round 0, p0 (s only)
+  mulwide(hs ^ j ^ STREAM_KEY1, PHILOX_M1, h1, l1);                         // round 1, p1
+  mulwide(h1 ^ (STREAM_KEY0 + PHILOX_W0), PHILOX_M0, h0, l0);               // round 2, p0
+  BlockConst c;
+  c.a = l1 ^ (STREAM_KEY0 + 2u * PHILOX_W0);
   c.b = h0 ^ (STREAM_KEY1 + 2u * PHILOX_W1);
   c.c3 = l0;
   return c;
 }
 
 __device__ __forceinline__ LaneShared lane_shared(uint32_t sseed, uint32_t k) {
-  uint32_t h0, l0, h1, l1;
-  mulwide(k ^ sseed, PHILOX_M0, h0, l0);                              // round 1, p0
-  mulwide(h0 ^ (STREAM_KEY1 + PHILOX_W1), PHILOX_M1, h1, l1);         // round 2, p1
+  uint32_t hs, ls, h0, l0, h1, l1;
+  mulwide(sseed, PHILOX_M0, hs, ls);                                        // round 0, p0 (loop invariant)
+  mulwide(k ^ STREAM_KEY0, PHILOX_M0, h0, l0);                              // round 1, p0
+  mulwide(h0 ^ ls ^ (STREAM_KEY1 + PHILOX_W1), PHILOX_M1, h1, l1);          // round 2, p1
   LaneShared s;
   s.h = h1; s.l = l1; s.l0 = l0;
   return s;
 }
 
 // rounds 3..9 from the factored state
-__device__ __forceinline__ void stream_block_tail(uint32_t sseed, const LaneShared& ls, const QuadConst& qc, uint32_t (&o)[4]) {
-  uint32_t c0 = ls.h ^ qc.a, c1 = ls.l, c2 = ls.l0 ^ qc.b, c3 = qc.c3;
+__device__ __forceinline__ void stream_block_tail(const LaneShared& ls, const BlockConst& bc, uint32_t (&o)[4]) {
+  uint32_t c0 = ls.h ^ bc.a, c1 = ls.l, c2 = ls.l0 ^ bc.b, c3 = bc.c3;
 #pragma unroll
   for (int r = 3; r < 10; ++r) {
     uint32_t h0, l0, h1, l1;
     mulwide(c0, PHILOX_M0, h0, l0);
     mulwide(c2, PHILOX_M1, h1, l1);
-    uint32_t n0 = h1 ^ c1 ^ (sseed + (uint32_t)r * PHILOX_W0);
+    uint32_t n0 = h1 ^ c1 ^ (STREAM_KEY0 + (uint32_t)r * PHILOX_W0);
     uint32_t n2 = h0 ^ c3 ^ (STREAM_KEY1 + (uint32_t)r * PHILOX_W1);
     c0 = n0; c1 = l1; c2 = n2; c3 = l0;
   }
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
+
+// quad 3 of a unit: top bytes of word i of blocks 0, 1, 2 -> bits 0-7, 8-15, 16-23 (two PRMT per word)
+__device__ __forceinline__ uint32_t harvest01(uint32_t w0, uint32_t w1) { return __byte_perm(w0, w1, 0x0073); }
+__device__ __forceinline__ uint32_t harvest2(uint32_t t01, uint32_t w2) { return __byte_perm(t01, w2, 0x0710); }
 
 // Bits of 1.0f, read from constant memory so that ptxas keeps them in a REGISTER: LOP3 has one immediate
 // slot, so `(x & 0x7fffff) | 0x3f800000` with two literals costs two LOP3 per Philox word; with the
@@ -102,16 +126,12 @@ __device__ __forceinline__ void stream_block_tail(uint32_t sseed, const LaneShar
 static __constant__ uint32_t c_one_bits = 0x3f800000u;
 
 __device__ __forceinline__ float mantissa_to_1_2(uint32_t x) {
-#ifdef CWQ_TWO_LOP_MASK
-  return __uint_as_float((x & 0x007fffffu) | 0x3f800000u);
-#else
   uint32_t r;
   asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(r) : "r"(x), "r"(c_one_bits));
   return __uint_as_float(r);
-#endif
 }
 
-// Two N(0,1) values from two Philox words (Box-Muller, 23-bit uniforms).
+// Two N(0,1) values from two uniform words (Box-Muller, 23-bit uniforms).
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, float& zo) {
   float f1 = mantissa_to_1_2(xa);  // [1,2)
   float f2 = mantissa_to_1_2(xb);
@@ -127,18 +147,69 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, 
   zo = __fmul_rn(r, s);
 }
 
-__device__ __forceinline__ void normal_quad_tail(uint32_t sseed, const LaneShared& ls, const QuadConst& qc, float (&z)[4]) {
-  uint32_t o[4];
-  stream_block_tail(sseed, ls, qc, o);
-  box_muller(o[0], o[1], z[0], z[1]);
-  box_muller(o[2], o[3], z[2], z[3]);
+__device__ __forceinline__ void box_muller_quad(const uint32_t (&w)[4], float (&z)[4]) {
+  box_muller(w[0], w[1], z[0], z[1]);
+  box_muller(w[2], w[3], z[2], z[3]);
 }
 
-__device__ __forceinline__ void normal_quad(uint32_t sseed, uint32_t k, uint32_t q, float (&z)[4]) {
-  uint32_t o[4];
-  stream_block(sseed, k, q, o);
-  box_muller(o[0], o[1], z[0], z[1]);
-  box_muller(o[2], o[3], z[2], z[3]);
+// The NQ (1..4) quads of one unit of candidate k: f(quad_in_unit, z[4]) is called for each, in order.
+// bc(b) returns the BlockConst of the unit's block b.  Everything stays in registers.
+template <int NQ, class GetBC, class F>
+__device__ __forceinline__ void unit_quads(const LaneShared& ls, GetBC&& bc, F&& f) {
+  constexpr int NB = NQ < 3 ? NQ : 3;
+  uint32_t v[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    uint32_t o[4];
+    stream_block_tail(ls, bc(b), o);
+    if (NQ == 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = b == 0 ? o[i] : (b == 1 ? harvest01(v[i], o[i]) : harvest2(v[i], o[i]));
+    }
+    float z[4];
+    box_muller_quad(o, z);
+    f(b, z);
+  }
+  if (NQ == 4) {
+    float z[4];
+    box_muller_quad(v, z);
+    f(3, z);
+  }
+}
+
+// All nq quads of candidate k's row: f(quad, z[4]) in quad order; bc(j) = BlockConst of row block j.
+template <class GetBC, class F>
+__device__ __forceinline__ void row_quads(const LaneShared& ls, int nq, GetBC&& bc, F&& f) {
+  int Q = 0, j = 0;
+  for (; Q + 4 <= nq; Q += 4, j += 3)
+    unit_quads<4>(ls, [&](int b) { return bc(j + b); }, [&](int qi, const float (&z)[4]) { f(Q + qi, z); });
+  switch (nq - Q) {
+    case 1: unit_quads<1>(ls, [&](int b) { return bc(j + b); }, [&](int qi, const float (&z)[4]) { f(Q + qi, z); }); break;
+    case 2: unit_quads<2>(ls, [&](int b) { return bc(j + b); }, [&](int qi, const float (&z)[4]) { f(Q + qi, z); }); break;
+    case 3: unit_quads<3>(ls, [&](int b) { return bc(j + b); }, [&](int qi, const float (&z)[4]) { f(Q + qi, z); }); break;
+    default: break;
+  }
+}
+
+// One quad of a row, straight from the definition (decode / replay / debug kernels: O(N) work).
+__device__ __forceinline__ void quad_words(uint32_t sseed, uint32_t k, uint32_t quad, uint32_t (&w)[4]) {
+  const uint32_t u = quad >> 2, qi = quad & 3u;
+  if (qi < 3u) {
+    stream_block(sseed, k, 3u * u + qi, w);
+  } else {
+    uint32_t o0[4], o1[4], o2[4];
+    stream_block(sseed, k, 3u * u, o0);
+    stream_block(sseed, k, 3u * u + 1u, o1);
+    stream_block(sseed, k, 3u * u + 2u, o2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = harvest2(harvest01(o0[i], o1[i]), o2[i]);
+  }
+}
+
+__device__ __forceinline__ void normal_quad(uint32_t sseed, uint32_t k, uint32_t quad, float (&z)[4]) {
+  uint32_t w[4];
+  quad_words(sseed, k, quad, w);
+  box_muller_quad(w, z);
 }
 
 // Deterministic natural log / exp (Cephes-style minimax polynomials), bit-identical to

@@ -174,7 +174,7 @@ CWQ_API int cwq_ac_decode_host(const int64_t* h_counts, int32_t n_symbols, const
 /* ---- the candidate stream (debug / oracle injection seam, misc.py:3-17) ---------------------- */
 /* rows k0..k0+nk-1, G columns, of the N(0,1) table of stream `stream_seed`: out[nk * G] */
 CWQ_API int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, float* out, void* stream);
-/* the raw Philox words of blocks (k0..k0+nk-1) x (0..nq-1): out[nk * nq * 4] */
+/* the raw Philox words of blocks j = 0..nq-1 of rows k0..k0+nk-1 (block(s,k,j)): out[nk * nq * 4] */
 CWQ_API int cwq_stream_words(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out, void* stream);
 /* plain Philox4x32-10 on n (counter, key) pairs: ctr[4n], key[2n], out[4n] */
 CWQ_API int cwq_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n, void* stream);

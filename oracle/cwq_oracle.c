@@ -58,10 +58,20 @@ void cwqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* ---- the normal stream z(stream_seed, k, d): spec section 3.2 ----
- * block(k, q) = philox(ctr = (0, k, 0, q), key = (stream_seed, 42)); lanes (0,1) -> dims 4q, 4q+1;
- * lanes (2,3) -> dims 4q+2, 4q+3.  The oracle evaluates the float transform with libm; the engine
- * uses MUFU approximations, so engine draws are injected when bit-exact indices are asserted. */
+/* ---- the normal stream z(stream_seed, k, d): DESIGN.md section 3.1 ----
+ * block(s, k, j) = philox(ctr = (s, k, 0, j), key = (STREAM_KEY0, 42)).  A row is cut into units of 16 dims;
+ * unit u owns blocks 3u, 3u+1, 3u+2.  Quad b < 3 of the unit uses the low 23 bits of the four words of block
+ * 3u+b; quad 3 uses, for word i, the top bytes of word i of the three blocks (block 3u in bits 0-7, 3u+1 in
+ * bits 8-15, 3u+2 in bits 16-23; low 23 bits taken).  Words (0,1) of a quad -> dims 4q, 4q+1; (2,3) -> dims
+ * 4q+2, 4q+3.  The oracle evaluates the float transform with libm; the engine uses MUFU approximations, so
+ * engine draws are injected when bit-exact indices are asserted. */
+#define STREAM_KEY0 0x6A09E667u
+
+static inline void stream_block(uint32_t sseed, uint32_t k, uint32_t j, uint32_t o[4]) {
+  uint32_t ctr[4] = {sseed, k, 0u, j}, key[2] = {STREAM_KEY0, STREAM_KEY1};
+  cwqo_philox4x32_10(ctr, key, o);
+}
+
 static inline void box_muller(uint32_t xa, uint32_t xb, float* ze, float* zo) {
   float f1 = u2f((xa & 0x007fffffu) | 0x3f800000u); /* [1,2) */
   float f2 = u2f((xb & 0x007fffffu) | 0x3f800000u);
@@ -73,30 +83,65 @@ static inline void box_muller(uint32_t xa, uint32_t xb, float* ze, float* zo) {
   *zo = r * sinf(th);
 }
 
-static inline void normal_quad(uint32_t sseed, uint32_t k, uint32_t q, float z[4]) {
-  uint32_t ctr[4] = {0u, k, 0u, q}, key[2] = {sseed, STREAM_KEY1}, o[4];
-  cwqo_philox4x32_10(ctr, key, o);
-  box_muller(o[0], o[1], &z[0], &z[1]);
-  box_muller(o[2], o[3], &z[2], &z[3]);
+static inline uint32_t harvest(uint32_t w0, uint32_t w1, uint32_t w2) {
+  return (w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16);
+}
+
+/* the four uniform words of quad `quad` of row k, straight from the definition */
+static inline void quad_words(uint32_t sseed, uint32_t k, uint32_t quad, uint32_t w[4]) {
+  uint32_t u = quad >> 2, qi = quad & 3u;
+  if (qi < 3u) { stream_block(sseed, k, 3u * u + qi, w); return; }
+  uint32_t o0[4], o1[4], o2[4];
+  stream_block(sseed, k, 3u * u, o0);
+  stream_block(sseed, k, 3u * u + 1u, o1);
+  stream_block(sseed, k, 3u * u + 2u, o2);
+  for (int i = 0; i < 4; ++i) w[i] = harvest(o0[i], o1[i], o2[i]);
+}
+
+static inline void normal_quad(uint32_t sseed, uint32_t k, uint32_t quad, float z[4]) {
+  uint32_t w[4];
+  quad_words(sseed, k, quad, w);
+  box_muller(w[0], w[1], &z[0], &z[1]);
+  box_muller(w[2], w[3], &z[2], &z[3]);
+}
+
+/* Same values as normal_quad for callers that walk the quads of ONE row in order (0, 1, 2, ...): the three
+ * blocks of the current unit are kept in `unit` so that quad 3 does not recompute them (the candidate loops
+ * timed as the CPU baseline do the same work per candidate as the GPU kernels: 3 blocks per 16 dims). */
+static inline void normal_quad_seq(uint32_t sseed, uint32_t k, uint32_t quad, uint32_t unit[3][4], float z[4]) {
+  uint32_t qi = quad & 3u, w[4];
+  if (qi < 3u) {
+    stream_block(sseed, k, 3u * (quad >> 2) + qi, unit[qi]);
+    memcpy(w, unit[qi], sizeof(w));
+  } else {
+    for (int i = 0; i < 4; ++i) w[i] = harvest(unit[0][i], unit[1][i], unit[2][i]);
+  }
+  box_muller(w[0], w[1], &z[0], &z[1]);
+  box_muller(w[2], w[3], &z[2], &z[3]);
 }
 
 /* rows k0..k0+nk-1, columns 0..G-1, row-major [nk, G]  (misc.py:10-15 with loc=0, scale=1) */
 void cwqo_normals(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, float* out) {
-  for (uint32_t i = 0; i < nk; ++i)
+  for (uint32_t i = 0; i < nk; ++i) {
+    uint32_t unit[3][4];
     for (uint32_t q = 0; q * 4 < G; ++q) {
       float z[4];
-      normal_quad(sseed, k0 + i, q, z);
+      normal_quad_seq(sseed, k0 + i, q, unit, z);
       for (uint32_t j = 0; j < 4 && q * 4 + j < G; ++j) out[(size_t)i * G + q * 4 + j] = z[j];
     }
+  }
 }
 
-/* raw Philox words of the same blocks, for the integer KAT / engine-vs-oracle bit check */
-void cwqo_stream_words(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out) {
+/* raw Philox words of blocks j = 0..nb-1 of rows k0..k0+nk-1, for the integer KAT / engine-vs-oracle bit check */
+void cwqo_stream_words(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t nb, uint32_t* out) {
   for (uint32_t i = 0; i < nk; ++i)
-    for (uint32_t q = 0; q < nq; ++q) {
-      uint32_t ctr[4] = {0u, k0 + i, 0u, q}, key[2] = {sseed, STREAM_KEY1};
-      cwqo_philox4x32_10(ctr, key, out + ((size_t)i * nq + q) * 4);
-    }
+    for (uint32_t j = 0; j < nb; ++j) stream_block(sseed, k0 + i, j, out + ((size_t)i * nb + j) * 4);
+}
+
+/* the uniform words (before the 23-bit mask) of quads 0..nq-1 of rows k0..k0+nk-1 */
+void cwqo_quad_words(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out) {
+  for (uint32_t i = 0; i < nk; ++i)
+    for (uint32_t q = 0; q < nq; ++q) quad_words(sseed, k0 + i, q, out + ((size_t)i * nq + q) * 4);
 }
 
 /* ---- deterministic log / exp (Cephes-style polynomials, explicit fmaf): spec section 3.3 ---- */
@@ -247,10 +292,11 @@ uint32_t cwqo_is_encode_group(const float* a, const float* b, int32_t G, uint32_
   int32_t nq = (G + 3) / 4;
   for (uint32_t k = 0; k < K; ++k) {
     float acc0 = 0.0f, acc1 = 0.0f;
+    uint32_t unit[3][4];
     for (int32_t q = 0; q < nq; ++q) {
       float z[4];
       if (inj) { for (int j = 0; j < 4; ++j) z[j] = (q * 4 + j < G) ? inj[(size_t)k * G + q * 4 + j] : 0.0f; }
-      else normal_quad(sseed, k, (uint32_t)q, z);
+      else normal_quad_seq(sseed, k, (uint32_t)q, unit, z);
       for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
         int d = q * 4 + j;
         float w = fmaf(a[d], z[j], b[d]);
@@ -334,10 +380,11 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, int32_t 
     uint32_t best_k = 0;
     for (uint32_t k = 0; k < n_samples; ++k) {
       float acc0 = 0.0f, acc1 = 0.0f;
+      uint32_t unit[3][4];
       for (int32_t q = 0; q < nq; ++q) {
         float z[4];
         if (inj) { for (int j = 0; j < 4; ++j) z[j] = (q * 4 + j < G) ? inj[((size_t)step * n_samples + k) * G + q * 4 + j] : 0.0f; }
-        else normal_quad(ss, k, (uint32_t)q, z);
+        else normal_quad_seq(ss, k, (uint32_t)q, unit, z);
         for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
           int d = q * 4 + j;
           float u = fmaf(z[j], c[d], e[d]);

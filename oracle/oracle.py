@@ -110,10 +110,23 @@ def philox4x32_10(ctr, key):
     return out
 
 
-def stream_words(stream_seed, k0, nk, nq):
-    out = np.zeros((nk, nq, 4), dtype=np.uint32)
+STREAM_KEY = (0x6A09E667, 42)   # block(s, k, j) = philox(ctr = (s, k, 0, j), key = STREAM_KEY)
+
+
+def stream_words(stream_seed, k0, nk, nb):
+    """Raw Philox words of blocks 0..nb-1 of rows k0..k0+nk-1: uint32[nk, nb, 4]."""
+    out = np.zeros((nk, nb, 4), dtype=np.uint32)
     lib().cwqo_stream_words(ctypes.c_uint32(_u32(stream_seed)), ctypes.c_uint32(_u32(k0)), ctypes.c_uint32(nk),
-                            ctypes.c_uint32(nq), _p(out, _c_u32p))
+                            ctypes.c_uint32(nb), _p(out, _c_u32p))
+    return out
+
+
+def quad_words(stream_seed, k0, nk, nq):
+    """The four uniform words (before the 23-bit mask) of quads 0..nq-1 of rows k0..k0+nk-1: uint32[nk, nq, 4].
+    Quads 0-2 of a 16-dim unit are the unit's three blocks, quad 3 is harvested from their top bytes."""
+    out = np.zeros((nk, nq, 4), dtype=np.uint32)
+    lib().cwqo_quad_words(ctypes.c_uint32(_u32(stream_seed)), ctypes.c_uint32(_u32(k0)), ctypes.c_uint32(nk),
+                          ctypes.c_uint32(nq), _p(out, _c_u32p))
     return out
 
 

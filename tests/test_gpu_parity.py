@@ -62,6 +62,11 @@ def test_draws_match_libm_box_muller(cwq, oracle):
     # ragged G and row offsets address the same table
     z5 = E.draw_candidates(42, 100, 7, 5).cpu().numpy()
     assert np.array_equal(z5, z[100:107, :5])
+    # several 16-dim units (greedy-sized rows): blocks 3u..3u+2 and the harvested fourth quad of every unit
+    for G in (13, 17, 48, 61, 547):
+        zg = E.draw_candidates(1000 * 43 + 5, 16000, 300, G).cpu().numpy()
+        zo = oracle.default_normal_source(1000 * 43 + 5, 16000, 300, G)
+        assert np.abs(zg - zo).max() < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------

@@ -21,11 +21,33 @@ def test_philox4x32_10_known_answers(oracle):
         assert list(oracle.philox4x32_10(ctr, key)) == want
 
 
-def test_stream_is_philox_on_counter_0_k_0_q(oracle):
-    w = oracle.stream_words(42, 7, 3, 2)
+def test_stream_blocks_are_philox_on_counter_s_k_0_j(oracle):
+    w = oracle.stream_words(42, 7, 3, 5)
     for i in range(3):
-        for q in range(2):
-            assert list(w[i, q]) == list(oracle.philox4x32_10([0, 7 + i, 0, q], [42, 42]))
+        for j in range(5):
+            assert list(w[i, j]) == list(oracle.philox4x32_10([42, 7 + i, 0, j], [0x6A09E667, 42]))
+
+
+def test_stream_units_three_blocks_plus_harvested_quad(oracle):
+    """unit u of a row owns blocks 3u..3u+2; quads 0-2 are those blocks, quad 3 is made of the
+    top bytes of the three blocks (block 3u in bits 0-7, 3u+1 in bits 8-15, 3u+2 in bits 16-23)."""
+    seed, k0, nk = 1000 * 45 + 3, 16380, 6
+    blocks = oracle.stream_words(seed, k0, nk, 9)
+    quads = oracle.quad_words(seed, k0, nk, 11)          # 2 full units + 3 quads
+    for u in range(3):
+        for b in range(3):
+            if 4 * u + b < 11:
+                assert np.array_equal(quads[:, 4 * u + b], blocks[:, 3 * u + b])
+    for u in range(2):
+        top = blocks[:, 3 * u:3 * u + 3] >> 24
+        assert np.array_equal(quads[:, 4 * u + 3], top[:, 0] | (top[:, 1] << 8) | (top[:, 2] << 16))
+    # the normals are Box-Muller of the low 23 bits of those words (float64 here, libm float32 in the oracle)
+    z = oracle.default_normal_source(seed, k0, nk, 44)
+    m = (quads & 0x7FFFFF).astype(np.float64) / 2.0 ** 23
+    u1, th = 1.0 - m[..., 0::2], 2 * np.pi * m[..., 1::2] - np.pi
+    r = np.sqrt(-2 * np.log(u1))
+    want = np.stack([r * np.cos(th), r * np.sin(th)], -1).reshape(nk, 44)
+    assert np.abs(z - want).max() < 2e-5
 
 
 def test_normal_stream_statistics_and_addressing(oracle):
