@@ -85,10 +85,7 @@ def decode_importance_sample(sample_index, p_loc, p_scale, seed, use_index=False
 # ----------------------------------------------------------------------------------------------
 # grouped entry points
 # ----------------------------------------------------------------------------------------------
-def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, stage,
-                  shard=None):
-    """Shared driver.  stage: 'groups' | 'indices' | 'full'.  Returns (job, per-segment sizes)."""
-    dev = E.cuda_device()
+def _batch_specs(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit):
     ns = len(targets)
 
     def per(v):
@@ -99,11 +96,22 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
         _check_dtype(t, "Target")
         _check_dtype(p, "Proposal")
     sizes = [int(np.prod(np.shape(p.loc))) if not hasattr(p.loc, "numel") else int(p.loc.numel()) for p in proposals]
-    specs = [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
-    q_loc = E.concat_to_device([t.loc for t in targets], dev, "Target")
-    q_scale = E.concat_to_device([t.scale for t in targets], dev, "Target")
-    p_loc = E.concat_to_device([p.loc for p in proposals], dev, "Proposal")
-    p_scale = E.concat_to_device([p.scale for p in proposals], dev, "Proposal")
+    return [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
+
+
+def _upload(targets, proposals, dev):
+    return (E.concat_to_device([t.loc for t in targets], dev, "Target"),
+            E.concat_to_device([t.scale for t in targets], dev, "Target"),
+            E.concat_to_device([p.loc for p in proposals], dev, "Proposal"),
+            E.concat_to_device([p.scale for p in proposals], dev, "Proposal"))
+
+
+def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, stage,
+                  shard=None):
+    """Shared driver.  stage: 'groups' | 'indices' | 'full'.  Returns the job with its group tables synchronised."""
+    dev = E.cuda_device()
+    specs = _batch_specs(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
+    q_loc, q_scale, p_loc, p_scale = _upload(targets, proposals, dev)
     job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs).prepare(sync=shard is not None)
     if stage == "groups":
         return job.sync_groups()
@@ -134,22 +142,94 @@ def _segment_result(job, s, host, return_indices):
 
 def _host_views(job, with_bits):
     """One batch of device->host copies for everything the caller gets back."""
-    off = job.seg_outlier_off.cpu().numpy()
-    n_out = int(off[-1])
-    names = ["sample", "starts", "index", "outlier_idx", "outlier_q"]
-    tensors = [job.sample, job.groups.starts, job.index, job.outlier_idx[:n_out], job.outlier_q[:n_out]]
+    ng = job.groups.n_groups
     if with_bits:
-        names += ["bit_off", "bits"]
-        tensors += [job.bit_off, job.bits]
+        counts = torch.cat([job.seg_outlier_off[-1:], job.bit_off[ng:ng + 1]]).cpu().numpy()
+        off_tail, total_bits = int(counts[0]), int(counts[1])
+    else:
+        off_tail, total_bits = int(job.seg_outlier_off[-1:].cpu().numpy()[0]), 0
+    n_out = off_tail
+    names = ["sample", "starts", "index", "outlier_idx", "outlier_q", "seg_outlier_off"]
+    tensors = [job.sample, job.groups.starts, job.index, job.outlier_idx[:n_out], job.outlier_q[:n_out], job.seg_outlier_off]
+    if with_bits:
+        # packed bits -> the reference's '0'/'1' characters on the device, once for the whole batch
+        names += ["bit_off", "ascii"]
+        tensors += [job.bit_off, E.device_bits_to_ascii(job.bits, total_bits)]
     host = dict(zip(names, E.to_host(tensors)))
-    host["seg_outlier_off"] = off
     host["index"] = host["index"].view(np.uint32)
     host["outlier_q"] = host["outlier_q"].view(np.uint16)
-    if with_bits:
-        total_bits = int(host["bit_off"][-1])
-        # packed MSB-first bits -> the reference's '0'/'1' characters, once for the whole batch
-        host["ascii"] = np.unpackbits(host["bits"][:(total_bits + 7) // 8])[:total_bits] + np.uint8(48)
     return host
+
+
+# A batch above this many dims is cut into chunks of whole calls that flow through a three-stage pipeline
+# (upload on a copy stream | kernels on the current stream | download + host formatting), so that host<->device
+# copies and the host-side bit formatting of one chunk overlap the scoring kernel of the next.
+PIPELINE_MIN_DIMS = 1 << 21
+PIPELINE_CHUNKS = 4
+
+
+def _plan_chunks(sizes, n_chunks):
+    """Consecutive runs of calls: list of (first, last + 1).  The first and the last chunk get a third of the
+    dims of the inner ones: the upload of the first and the download + formatting of the last are the only
+    stages nothing overlaps."""
+    if n_chunks <= 1 or len(sizes) <= 1:
+        return [(0, len(sizes))]
+    weights = [1.0] + [3.0] * (n_chunks - 2) + [1.0] if n_chunks > 2 else [1.0, 1.0]
+    total, wsum = float(sum(sizes)), float(sum(weights))
+    targets = np.cumsum(weights)[:-1] * total / wsum
+    bounds, acc, start = [], 0, 0
+    for i, n in enumerate(sizes):
+        acc += n
+        if len(bounds) < len(targets) and acc >= targets[len(bounds)] and i + 1 < len(sizes):
+            bounds.append((start, i + 1))
+            start = i + 1
+    bounds.append((start, len(sizes)))
+    return bounds
+
+
+_side_streams = {}
+
+
+def _copy_streams(dev):
+    """One upload and one download stream per device, created once: torch's caching allocator keeps a pool per
+    stream, so fresh streams on every call would turn every buffer into a new cudaMalloc."""
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _side_streams[key]
+
+
+def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices):
+    dev = E.cuda_device()
+    compute = torch.cuda.current_stream()
+    up, down = _copy_streams(dev)
+    up.wait_stream(compute)
+    staged = []
+    with torch.cuda.stream(up):                      # stage 1: every chunk's inputs, in order, on the copy stream
+        for a, b in chunks:
+            tensors = _upload(targets[a:b], proposals[a:b], dev)
+            ev = torch.cuda.Event()
+            ev.record(up)
+            staged.append((tensors, ev))
+    jobs = []
+    for (a, b), (tensors, ev) in zip(chunks, staged):  # stage 2: kernels, no host synchronisation in between
+        compute.wait_event(ev)
+        for t in tensors:
+            t.record_stream(compute)
+        job = E.ISJob(*tensors, specs[a:b]).prepare(sync=False)
+        job.encode().decode().pack()
+        done = torch.cuda.Event()
+        done.record(compute)
+        jobs.append((job, done))
+    results = []
+    for job, done in jobs:                           # stage 3: per chunk, while later chunks are still being scored
+        down.wait_event(done)
+        with torch.cuda.stream(down):
+            job.sync_groups()
+            host = _host_views(job, with_bits=not return_indices)
+        results += [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+    compute.wait_stream(down)
+    return results
 
 
 def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits=4,
@@ -158,6 +238,13 @@ def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_gr
     dim_kl_bit_limit may be scalars or per-call lists.  Returns a list with, per call, exactly what
     code_grouped_importance_sample returns.  `shard` (see distributed.py) replaces the single-GPU
     encode stage by a sharded one."""
+    if shard is None and len(targets) > 1:
+        specs = _batch_specs(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
+        sizes = [sp.n for sp in specs]
+        if sum(sizes) >= PIPELINE_MIN_DIMS and min(sizes) > 0:
+            chunks = _plan_chunks(sizes, PIPELINE_CHUNKS)
+            if len(chunks) > 1:
+                return _encode_batch_pipelined(list(targets), list(proposals), specs, chunks, return_indices)
     job = _encode_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, "full",
                         shard=shard)
     host = _host_views(job, with_bits=not return_indices)

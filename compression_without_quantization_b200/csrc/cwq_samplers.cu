@@ -130,7 +130,7 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 // SMALL: every group has <= 16 dims (the reference defaults): only the register-resident path is compiled in,
 // which keeps the kernel at 64 registers / 4 resident CTAs per SM (measured best).
 template <bool SMALL>
-__global__ void __launch_bounds__(IS_THREADS, SMALL ? 4 : 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
+__global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
                                                          long long g0, long long ng, const long long* __restrict__ ng_dev,
                                                          const ull* __restrict__ unit_off,
@@ -569,6 +569,21 @@ __global__ void __launch_bounds__(256) k_fixed_unpack(const uint8_t* __restrict_
   index[i] = v;
 }
 
+// packed MSB-first bits -> the reference's '0'/'1' characters (what BIO:76-79 consumes), 8 characters per thread.
+// `ascii` holds 8 * ceil(n_bits / 8) bytes: the last thread may write up to 7 characters past n_bits.
+__global__ void __launch_bounds__(256) k_bits_to_ascii(const uint8_t* __restrict__ bits, long long n_bytes, uint2* __restrict__ ascii) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bytes) return;
+  const uint32_t b = bits[i];
+  uint32_t lo = 0x30303030u, hi = 0x30303030u;   // characters 0-3 (bits 7..4) and 4-7 (bits 3..0), little-endian words
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    lo |= ((b >> (7 - c)) & 1u) << (8 * c);
+    hi |= ((b >> (3 - c)) & 1u) << (8 * c);
+  }
+  ascii[i] = make_uint2(lo, hi);
+}
+
 // ------------------------------------------------------------------------------------------
 // the candidate stream, materialised (debug / oracle injection)
 // ------------------------------------------------------------------------------------------
@@ -877,6 +892,16 @@ extern "C" int cwq_fixed_pack(const uint32_t* index, int64_t count, int32_t bits
 extern "C" int cwq_fixed_unpack(const uint8_t* bits, int64_t count, int32_t bits_per_index, uint32_t* index, void* stream) {
   CWQ_REQUIRE(count > 0 && bits_per_index >= 1 && bits_per_index <= 32, "bad sizes");
   k_fixed_unpack<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, count, bits_per_index, index);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, uint8_t* ascii, void* stream) {
+  CWQ_REQUIRE(n_bits >= 0 && (n_bits == 0 || (bits && ascii)), "bad arguments");
+  CWQ_REQUIRE((reinterpret_cast<uintptr_t>(ascii) & 7u) == 0, "ascii must be 8-byte aligned");
+  if (n_bits == 0) return CWQ_OK;
+  const long long n_bytes = (n_bits + 7) / 8;
+  k_bits_to_ascii<<<(unsigned)((n_bytes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, n_bytes, reinterpret_cast<uint2*>(ascii));
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }

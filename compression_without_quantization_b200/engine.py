@@ -136,7 +136,12 @@ class SegmentTable:
             off += sp.n
         self.n = off
         self.starts = [int(s.start) for s in self.host]
-        self.dev = torch.frombuffer(bytearray(bytes(self.host)), dtype=torch.uint8).to(device)
+        # pinned staging + asynchronous copy: a pageable upload would block the host until everything already
+        # queued on the stream has run, which serialises the chunks of the batch pipeline
+        staging = torch.frombuffer(bytearray(bytes(self.host)), dtype=torch.uint8)
+        if torch.device(device).type == "cuda":
+            staging = staging.pin_memory()
+        self.dev = staging.to(device, non_blocking=True)
         self.max_size_limit = max(int(s.size_limit) for s in self.host)
 
 
@@ -235,6 +240,16 @@ def bits_to_ascii(bits_host, n_bits, bit_begin=0):
     u = np.unpackbits(bits_host[b0:b1])
     lo = bit_begin - 8 * b0
     return (u[lo:lo + n_bits] + np.uint8(48)).tobytes()
+
+
+def device_bits_to_ascii(bits, n_bits):
+    """Packed MSB-first bits on the device -> '0'/'1' characters on the device (uint8[n_bits]); the expansion runs at
+    HBM speed instead of costing the host an unpackbits pass per call."""
+    n_bits = int(n_bits)
+    out = torch.empty(8 * ((n_bits + 7) // 8), dtype=torch.uint8, device=bits.device)
+    if n_bits:
+        _lib.call("cwq_bits_to_ascii", _ptr(bits), n_bits, _ptr(out), _stream())
+    return out[:n_bits]
 
 
 def ascii_to_bits(code):

@@ -217,6 +217,41 @@ def test_is_batch_equals_separate_calls(cwq, syn):
         assert np.array_equal(batch[i][3][0], one[3][0]) and np.array_equal(batch[i][3][1], one[3][1])
 
 
+def test_is_pipelined_batch_equals_single_pass(cwq, syn, monkeypatch):
+    """Large batches are cut into chunks of whole calls that overlap copies, kernels and host formatting
+    (coded_importance_sampler._encode_batch_pipelined); the results must not depend on the cut."""
+    from compression_without_quantization_b200 import coded_importance_sampler as CIS
+    sizes = [900, 40, 1500, 1, 333, 2048, 7, 610]
+    data = [syn.synthetic_posterior(n, 70 + i, i % 3 == 1) for i, n in enumerate(sizes)]
+    # host tensors sliced from one pinned buffer, as bench.py passes them, and plain numpy arrays
+    import torch
+    flat = [torch.from_numpy(np.concatenate([d[j] for d in data])).pin_memory() for j in range(4)]
+    off = np.cumsum([0] + sizes)
+    variants = {
+        "numpy": ([syn.Normal(d[0], d[1]) for d in data], [syn.Normal(d[2], d[3]) for d in data]),
+        "pinned": ([syn.Normal(flat[0][off[i]:off[i + 1]], flat[1][off[i]:off[i + 1]]) for i in range(len(sizes))],
+                   [syn.Normal(flat[2][off[i]:off[i + 1]], flat[3][off[i]:off[i + 1]]) for i in range(len(sizes))]),
+    }
+    seeds, mg = [42, 42, 1, 2, 3, 4, 5, 6], [4, 2, 4, 4, 3, 4, 2, 4]
+    monkeypatch.setattr(CIS, "PIPELINE_MIN_DIMS", 1 << 62)
+    single = cwq.code_grouped_importance_sample_batch(*variants["numpy"], seeds, 13, mg, 10)
+    for n_chunks in (2, 3, 8):
+        monkeypatch.setattr(CIS, "PIPELINE_MIN_DIMS", 0)
+        monkeypatch.setattr(CIS, "PIPELINE_CHUNKS", n_chunks)
+        assert len(CIS._plan_chunks(sizes, n_chunks)) > 1
+        for name, (t, p) in variants.items():
+            piped = cwq.code_grouped_importance_sample_batch(t, p, seeds, 13, mg, 10)
+            assert len(piped) == len(single)
+            for a, b in zip(piped, single):
+                assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and a[1] == b[1]
+                assert np.array_equal(a[2], b[2])
+                assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
+        idx = cwq.code_grouped_importance_sample_batch(*variants["numpy"], seeds, 13, mg, 10, return_indices=True)
+        ref = [cwq.code_grouped_importance_sample(None, variants["numpy"][0][i], variants["numpy"][1][i], seeds[i], 13, mg[i], 10,
+                                                  return_indices=True) for i in range(len(sizes))]
+        assert all(list(a[1]) == list(b[1]) for a, b in zip(idx, ref))
+
+
 def test_is_per_group_entry_points(cwq, oracle, syn):
     rng = np.random.default_rng(0)
     for G, seed in [(16, 42), (5, 43), (1, 44)]:
