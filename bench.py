@@ -218,9 +218,9 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs).prepare(sync=world > 1)
+        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs).prepare(sync=False)
         if world > 1:
-            D.make_is_shard()(job)     # needs the per-group work on the host: one synchronisation after grouping
+            D.make_is_shard()(job)     # ranges + all-gather sizes are needed on the host: one synchronisation after grouping
         else:
             job.encode()               # N = 1: no host synchronisation anywhere inside the step
         job.decode().pack()
@@ -332,9 +332,9 @@ def main():
         "unit": "Tinstr/s", "frac": achieved / issue_peak,
         "sfu_frac": cd_per_s_kernel * SFU_PER_CD / sfu_peak,
         "frac_at_observed_clock": (achieved / (sms * 128 * f_obs)) if f_obs else None,
-        # ideal-independent-chains microbenchmark of this instruction mix: 26.7 cycles per warp-candidate-dim per
-        # sub-partition (tools/microbench/overlap.cu "kernel mix", profiles/r01_pipe_overlap_microbench.log)
-        "frac_of_measured_mix_ceiling": cd_per_s_kernel / (sms * 4 * 32 / 26.7 * f_max),
+        # ideal-independent-chains microbenchmark of this kernel's instruction mix: 23.6 cycles per warp-candidate-dim
+        # per sub-partition (tools/microbench/overlap.cu "v2 mix", profiles/r01_pipe_overlap_v2_mix.log)
+        "frac_of_measured_mix_ceiling": cd_per_s_kernel / (sms * 4 * 32 / 23.6 * f_max),
         "candidate_dims_per_sec_kernel": cd_per_s_kernel, "kernel_ms": score_ms_max,
         "kernel_share_of_step": score_ms_max / ms_per_step if ms_per_step > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on a 2-image

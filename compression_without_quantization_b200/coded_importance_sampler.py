@@ -112,7 +112,7 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
     dev = E.cuda_device()
     specs = _batch_specs(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
     q_loc, q_scale, p_loc, p_scale = _upload(targets, proposals, dev)
-    job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs).prepare(sync=shard is not None)
+    job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs).prepare(sync=shard is not None and not hasattr(shard, "plan_async"))
     if stage == "groups":
         return job.sync_groups()
     if shard is None:
@@ -199,7 +199,7 @@ def _copy_streams(dev):
     return _side_streams[key]
 
 
-def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices):
+def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, shard=None):
     dev = E.cuda_device()
     compute = torch.cuda.current_stream()
     up, down = _copy_streams(dev)
@@ -211,25 +211,56 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices):
             ev = torch.cuda.Event()
             ev.record(up)
             staged.append((tensors, ev))
-    jobs = []
-    for (a, b), (tensors, ev) in zip(chunks, staged):  # stage 2: kernels, no host synchronisation in between
+    n = len(chunks)
+    jobs, done, results = [None] * n, [None] * n, [None] * n
+
+    def group(i):                                    # stage 2a: prologue + grouping (+ this rank's range, sharded runs)
+        (a, b), (tensors, ev) = chunks[i], staged[i]
         compute.wait_event(ev)
         for t in tensors:
             t.record_stream(compute)
-        job = E.ISJob(*tensors, specs[a:b]).prepare(sync=False)
-        job.encode().decode().pack()
-        done = torch.cuda.Event()
-        done.record(compute)
-        jobs.append((job, done))
-    results = []
-    for job, done in jobs:                           # stage 3: per chunk, while later chunks are still being scored
-        down.wait_event(done)
+        jobs[i] = E.ISJob(*tensors, specs[a:b]).prepare(sync=False)
+        if shard is not None:
+            shard.plan_async(jobs[i], down)
+
+    def score(i):                                    # stage 2b: scoring (+ all-gather), decode, packing
+        job = jobs[i]
+        if shard is None:
+            job.encode()                             # group count stays on the device: nothing waits for the host
+        else:
+            shard.run_planned(job, shard.finish_plan(job))   # waits for the grouping of THIS chunk only
+        job.decode().pack()
+        done[i] = torch.cuda.Event()
+        done[i].record(compute)
+
+    def collect(i):                                  # stage 3: download + formatting while later chunks are scored
+        job = jobs[i]
+        down.wait_event(done[i])
         with torch.cuda.stream(down):
             job.sync_groups()
             host = _host_views(job, with_bits=not return_indices)
-        results += [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+        results[i] = [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+        jobs[i] = None
+
+    if shard is None:
+        for i in range(n):
+            group(i)
+            score(i)
+        for i in range(n):
+            collect(i)
+    else:
+        # the grouping of chunk i+1 is queued BEFORE the scoring of chunk i, so that the host can read its group
+        # counts (needed for the ranges and the all-gather sizes) while chunk i is being scored
+        group(0)
+        for i in range(n):
+            if i + 1 < n:
+                group(i + 1)
+            score(i)
+            if i >= 1:
+                collect(i - 1)
+        collect(n - 1)
     compute.wait_stream(down)
-    return results
+    return [r for chunk in results for r in chunk]
 
 
 def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits=4,
@@ -238,13 +269,13 @@ def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_gr
     dim_kl_bit_limit may be scalars or per-call lists.  Returns a list with, per call, exactly what
     code_grouped_importance_sample returns.  `shard` (see distributed.py) replaces the single-GPU
     encode stage by a sharded one."""
-    if shard is None and len(targets) > 1:
+    if len(targets) > 1 and (shard is None or hasattr(shard, "plan_async")):
         specs = _batch_specs(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
         sizes = [sp.n for sp in specs]
-        if sum(sizes) >= PIPELINE_MIN_DIMS and min(sizes) > 0:
+        if PIPELINE_MIN_DIMS <= sum(sizes) <= E.ASYNC_MAX_DIMS and min(sizes) > 0:
             chunks = _plan_chunks(sizes, PIPELINE_CHUNKS)
             if len(chunks) > 1:
-                return _encode_batch_pipelined(list(targets), list(proposals), specs, chunks, return_indices)
+                return _encode_batch_pipelined(list(targets), list(proposals), specs, chunks, return_indices, shard)
     job = _encode_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, "full",
                         shard=shard)
     host = _host_views(job, with_bits=not return_indices)

@@ -9,6 +9,21 @@ import torch
 import torch.distributed as dist
 
 
+def _cuts_on_device(work, world):
+    """world - 1 cut positions (int64 tensor on work's device) of the contiguous equal-work split: cut r closes range r at
+    the first group whose work prefix reaches r/world of the total.  Nothing here waits for the host."""
+    c = torch.cumsum(work.to(torch.float64), 0)
+    frac = torch.arange(1, world, dtype=torch.float64, device=c.device) / world
+    return torch.searchsorted(c, c[-1] * frac, right=False) + 1
+
+
+def _bounds_from_cuts(cuts, n, world):
+    b = [0] + [int(min(max(int(x), 0), n)) for x in cuts] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
 def balanced_ranges(work, world):
     """Split groups 0..len(work)-1 into `world` contiguous ranges with near-equal total work.
 
@@ -18,14 +33,7 @@ def balanced_ranges(work, world):
     n = int(w.numel())
     if world <= 1 or n == 0:
         return [0] + [n] * max(world, 1)
-    c = torch.cumsum(w.to(torch.float64), 0)
-    total = float(c[-1].item())
-    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64, device=c.device)
-    cuts = torch.searchsorted(c, targets, right=False) + 1  # first prefix reaching the target closes the range
-    b = [0] + [int(min(max(int(x), 0), n)) for x in cuts.cpu().tolist()] + [n]
-    for i in range(1, len(b)):
-        b[i] = max(b[i], b[i - 1])
-    return b
+    return _bounds_from_cuts(_cuts_on_device(w, world).cpu().tolist(), n, world)
 
 
 def all_gather_ranges(local, bounds, group=None):
@@ -47,27 +55,94 @@ def all_gather_ranges(local, bounds, group=None):
     return torch.cat([recv[r * longest:r * longest + lens[r]] for r in range(world)], 0)
 
 
+def row_blocks(sizes):
+    """Philox blocks per candidate of a group of `sizes` dims (3 blocks per 16 dims + tail)."""
+    nq = (sizes + 3) // 4
+    return 3 * (nq // 4) + torch.clamp(nq % 4, max=3)
+
+
 def is_work(job):
     """Per-group cost of the importance sampler: candidates x Philox blocks per candidate."""
     sizes = job.groups.starts[1:] - job.groups.starts[:-1]
-    return job.K.to(torch.int64) * torch.clamp((sizes + 3) // 4, min=1)
+    return job.K.to(torch.int64) * torch.clamp(row_blocks(sizes), min=1)
 
 
 def greedy_work(job):
     sizes = job.groups.starts[1:] - job.groups.starts[:-1]
-    return torch.clamp((sizes + 3) // 4, min=1)
+    return torch.clamp(row_blocks(sizes), min=1)
+
+
+class ISShard:
+    """Sharded encode stage of the importance sampler: this rank scores one contiguous, work-balanced range of groups and
+    one all-gather gives every rank all indices.
+
+    Called as `shard(job)` it needs the group tables on the host (one synchronisation after grouping).  The batch
+    pipeline uses the split form instead: `plan_async(job, side)` queues the range computation behind the grouping
+    and copies (cuts, group count, per-call group offsets) to the host on `side`, so the host learns them while the
+    PREVIOUS chunk is still being scored; `finish_plan(job)` then waits for that copy only."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def _world_rank(self):
+        if dist.is_initialized():
+            return dist.get_world_size(self.group), dist.get_rank(self.group)
+        return 1, 0
+
+    def __call__(self, job):
+        world, rank = self._world_rank()
+        g = job.groups
+        if hasattr(g, "synced") and not g.synced and job.K.is_cuda:
+            # group tables still device-only (prepare(sync=False)): ranges, group count and per-call offsets come
+            # over in ONE copy, i.e. one host synchronisation per step instead of two
+            self.plan_async(job, torch.cuda.current_stream())
+            bounds = self.finish_plan(job)
+        else:
+            bounds = balanced_ranges(is_work(job), world)
+        self.run_planned(job, bounds)
+
+    def run_planned(self, job, bounds):
+        world, rank = self._world_rank()
+        job.encode(bounds[rank], bounds[rank + 1])
+        job.index = all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, self.group).contiguous()
+        job.shard_bounds = bounds
+
+    def plan_async(self, job, side):
+        world, _ = self._world_rank()
+        g = job.groups
+        cap = int(job.K.numel())
+        ngd = g.n_groups_dev
+        sizes = g.starts[1:cap + 1] - g.starts[:cap]
+        work = job.K.to(torch.int64) * torch.clamp(row_blocks(sizes), min=1)
+        work = torch.where(torch.arange(cap, device=work.device) < ngd, work, torch.zeros_like(work))
+        parts = [ngd.to(torch.int64), g.seg_group_off.to(torch.int64)]
+        if world > 1:
+            parts.insert(0, torch.minimum(_cuts_on_device(work, world), ngd))
+        info = torch.cat(parts)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        host = torch.empty(info.shape, dtype=info.dtype, device="cpu", pin_memory=True)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host.copy_(info, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+        info.record_stream(side)
+        job._plan = (host, copied, world)
+
+    def finish_plan(self, job):
+        host, copied, world = job._plan
+        copied.synchronize()
+        v = host.numpy()
+        ng = int(v[world - 1])
+        job.groups.set_host(v[world:].copy())
+        job.sync_groups()
+        return _bounds_from_cuts(v[:world - 1].tolist(), ng, world)
 
 
 def make_is_shard(group=None):
-    """`shard` callable for code_grouped_importance_sample_batch: encode this rank's range, all-gather indices."""
-    def shard(job):
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        rank = dist.get_rank(group) if dist.is_initialized() else 0
-        bounds = balanced_ranges(is_work(job), world)
-        job.encode(bounds[rank], bounds[rank + 1])
-        job.index = all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, group).contiguous()
-        job.shard_bounds = bounds
-    return shard
+    """`shard` object for code_grouped_importance_sample_batch: encode this rank's range, all-gather indices."""
+    return ISShard(group)
 
 
 def make_greedy_shard(group=None):

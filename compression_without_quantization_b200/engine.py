@@ -171,10 +171,15 @@ class _Groups:
 
     def sync(self):
         if self._n_groups is None:
-            self.seg_group_off_host = self.seg_group_off.cpu().numpy()
-            self._n_groups = ng = int(self.seg_group_off_host[-1])
-            self.starts = self.starts[:ng + 1]
-            self.group_seed = self.group_seed[:ng]
+            self.set_host(self.seg_group_off.cpu().numpy())
+        return self
+
+    def set_host(self, seg_group_off_host):
+        """Install the host copy of the per-segment group offsets (however it was brought over) and trim the views."""
+        self.seg_group_off_host = np.asarray(seg_group_off_host, dtype=np.int64)
+        self._n_groups = ng = int(self.seg_group_off_host[-1])
+        self.starts = self.starts[:ng + 1]
+        self.group_seed = self.group_seed[:ng]
         return self
 
 

@@ -95,6 +95,13 @@ int main() {
   run<0, 10, 9, 25, 18>("kernel mix, products via FP64", sms, d_out);
   run<9, 10, 9, 25, 9>("kernel mix, half via FP64", sms, d_out);
   run<12, 10, 9, 25, 6>("kernel mix, third via FP64", sms, d_out);
+  // stream v2 (3 blocks + harvested quad per 16 dims): 44 IMAD.WIDE, 32 MUFU, ~74 ALU (6 L = 18 + 11 xor), 81 FP32 per 16 cd
+  run<11, 8, 6, 20>("v2 mix / 4 cd", sms, d_out);
+  run<11, 8, 0, 20>("v2 mix / 4 cd, no ALU", sms, d_out);
+  run<11, 0, 0, 20>("v2 mix / 4 cd, W+F", sms, d_out);
+  run<11, 8, 0, 0>("v2 mix / 4 cd, W+M", sms, d_out);
+  run<0, 8, 0, 20>("v2 mix / 4 cd, M+F", sms, d_out);
+  run<22, 16, 12, 40>("v2 mix / 8 cd", sms, d_out);
   run<14, 10, 9, 25>("3-block mix / 5 cd", sms, d_out);
   run<14, 10, 10, 25>("3-block mix / 5 cd, +3 ALU", sms, d_out);
   run<14, 10, 9, 23>("3-block mix / 5 cd, -2 FP", sms, d_out);

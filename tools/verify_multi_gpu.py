@@ -38,6 +38,13 @@ def digest(res):
 sharded = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard())
 single = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12)
 ok_is = digest(sharded) == digest(single)
+# the chunked pipeline (coded_importance_sampler._encode_batch_pipelined), sharded, at 2 and 3 chunks
+from compression_without_quantization_b200 import coded_importance_sampler as CIS  # noqa: E402
+CIS.PIPELINE_MIN_DIMS = 0
+for n_chunks in (2, 3):
+    CIS.PIPELINE_CHUNKS = n_chunks
+    ok_is = ok_is and digest(cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard())) == digest(single)
+CIS.PIPELINE_MIN_DIMS = 1 << 62
 gs = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6, shard=D.make_greedy_shard())
 g1 = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6)
 ok_gr = all(a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) for a, b in zip(gs, g1))
