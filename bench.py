@@ -338,8 +338,11 @@ def main():
         "candidate_dims_per_sec_kernel": cd_per_s_kernel, "kernel_ms": score_ms_max,
         "kernel_share_of_step": score_ms_max / ms_per_step if ms_per_step > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on a 2-image
-        # launch (4 046 592 B read, 0 B written; profiles/r01_is_score_ncu_summary.md), scaled to this launch's images
-        "traffic": 4046592.0 * args.images / 2.0 / (world if world > 1 else 1),
+        # launch (4 043 264 B read, 0 B written; profiles/r01_is_score_ncu_summary.md), scaled to this launch's images
+        "traffic": 4043264.0 * args.images / 2.0 / (world if world > 1 else 1),
+        # thread-instructions the kernel executes per candidate-dim (ncu smsp__inst_executed x 32 / candidate-dims); the
+        # 17.5 of `achieved` is SURVEY.md 8d's algorithmic count, kept as the reporting unit
+        "executed_instr_per_candidate_dim": 16.1,
         "algorithmic_bytes": 8.0 * n_total / world + 16.0 * n_groups / world,
         "peak_source": "{} SMs x 128 FP32 lanes x {:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); the path is on-chip "
                        "issue/SFU bound, not HBM or tensor bound (SURVEY.md 8d); pipe widths: profiles/r01_pipes_microbench*.log"
