@@ -218,12 +218,13 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs).prepare(sync=False)
+        job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs)
         if world > 1:
+            job.launch(_lib.STAGE_GROUP)
             D.make_is_shard()(job)     # ranges + all-gather sizes are needed on the host: one synchronisation after grouping
+            job.launch(_lib.STAGE_FINISH)
         else:
-            job.encode()               # N = 1: no host synchronisation anywhere inside the step
-        job.decode().pack()
+            job.launch(_lib.STAGE_GROUP | _lib.STAGE_SCORE | _lib.STAGE_FINISH)   # no host synchronisation inside the step
         return job
 
     # ---- device-resident throughput ----

@@ -27,6 +27,16 @@ class Segment(ctypes.Structure):
     ]
 
 
+class ISBuffers(ctypes.Structure):
+    """struct cwq_is_buffers (include/cwq.h): every output and the scratch of cwq_is_encode_pipeline."""
+    _fields_ = [(name, ctypes.c_void_p) for name in
+                ("kl", "coef", "mask", "gid", "sample", "outlier_idx", "outlier_q", "starts", "group_seed", "total_kl", "K",
+                 "index", "bit_off", "seg_group_off", "seg_outlier_off", "bits")] + [
+        ("bits_capacity_bytes", ctypes.c_size_t), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+
+
+STAGE_GROUP, STAGE_SCORE, STAGE_FINISH = 1, 2, 4
+
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
 _I32 = ctypes.c_int32
@@ -52,6 +62,8 @@ SIGNATURES = {
     "cwq_is_encode_workspace_bytes": (_SZ, [_I64]),
     "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _SZ, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "cwq_is_pipeline_workspace_bytes": (_SZ, [_I64, _I32]),
+    "cwq_is_encode_pipeline": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I32, _I64, _I32, _P, _P]),
     "cwq_outlier_workspace_bytes": (_SZ, [_I64]),
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "cwq_outlier_decode": (ctypes.c_int, [_P, _P, _P, _I64, _P]),

@@ -14,6 +14,7 @@ their arrays may be numpy, torch (CPU or CUDA) or any DLPack producer.  `sess` i
 import numpy as np
 import torch
 
+from . import _lib as L
 from . import engine as E
 from ._lib import CwqError
 from .binary_io import elias_delta_code, elias_delta_decode
@@ -112,11 +113,26 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
     dev = E.cuda_device()
     specs = _batch_specs(targets, proposals, seeds, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
     q_loc, q_scale, p_loc, p_scale = _upload(targets, proposals, dev)
-    job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs).prepare(sync=shard is not None and not hasattr(shard, "plan_async"))
+    job = E.ISJob(q_loc, q_scale, p_loc, p_scale, specs)
+    fused = job.n <= E.ASYNC_MAX_DIMS and (shard is None or hasattr(shard, "plan_async"))
+    if fused:
+        # one library call per stage set, group count on the device: nothing below waits for the host until the
+        # results are copied back (a sharded run waits once, for the ranges and the all-gather sizes)
+        if shard is None:
+            stages = {"groups": L.STAGE_GROUP, "indices": L.STAGE_GROUP | L.STAGE_SCORE,
+                      "full": L.STAGE_GROUP | L.STAGE_SCORE | L.STAGE_FINISH}[stage]
+            return job.launch(stages).sync_groups()
+        job.launch(L.STAGE_GROUP)
+        if stage != "groups":
+            shard(job)
+        if stage == "full":
+            job.launch(L.STAGE_FINISH)
+        return job.sync_groups()
+    job.prepare(sync=True)
     if stage == "groups":
         return job.sync_groups()
     if shard is None:
-        job.encode()          # nothing below waits for the host until the results are copied back
+        job.encode()
     else:
         shard(job)
     if stage == "indices":
@@ -219,17 +235,17 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         compute.wait_event(ev)
         for t in tensors:
             t.record_stream(compute)
-        jobs[i] = E.ISJob(*tensors, specs[a:b]).prepare(sync=False)
+        jobs[i] = E.ISJob(*tensors, specs[a:b]).launch(L.STAGE_GROUP)
         if shard is not None:
             shard.plan_async(jobs[i], down)
 
     def score(i):                                    # stage 2b: scoring (+ all-gather), decode, packing
         job = jobs[i]
         if shard is None:
-            job.encode()                             # group count stays on the device: nothing waits for the host
+            job.launch(L.STAGE_SCORE | L.STAGE_FINISH)       # group count stays on the device: nothing waits for the host
         else:
             shard.run_planned(job, shard.finish_plan(job))   # waits for the grouping of THIS chunk only
-        job.decode().pack()
+            job.launch(L.STAGE_FINISH)
         done[i] = torch.cuda.Event()
         done[i].record(compute)
 

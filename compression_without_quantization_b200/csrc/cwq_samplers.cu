@@ -874,6 +874,50 @@ extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, con
   return CWQ_OK;
 }
 
+extern "C" size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments) {
+  if (n <= 0 || n_segments <= 0) return 0;
+  const int64_t cap = n + n_segments;
+  size_t w = cwq_group_workspace_bytes(n, n_segments);
+  const size_t others[3] = {cwq_is_encode_workspace_bytes(cap), cwq_outlier_workspace_bytes(n), cwq_pack_workspace_bytes(cap)};
+  for (size_t o : others) w = o > w ? o : w;
+  return w;
+}
+
+extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale,
+                                      int64_t n, const cwq_segment* segments, const cwq_segment* h_segments, int32_t n_segments,
+                                      int64_t max_group_size, int32_t stages, const cwq_is_buffers* b, void* stream) {
+  CWQ_REQUIRE(b && n > 0 && n_segments > 0, "bad arguments");
+  CWQ_REQUIRE((stages & ~(CWQ_STAGE_GROUP | CWQ_STAGE_SCORE | CWQ_STAGE_FINISH)) == 0 && stages != 0, "unknown stage");
+  const int64_t cap = n + n_segments;
+  const int64_t* ng_dev = b->seg_group_off + n_segments;
+  int rc = CWQ_OK;
+  if (stages & CWQ_STAGE_GROUP) {
+    rc = cwq_is_prologue(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, b->kl, b->coef, b->mask, stream);
+    if (rc != CWQ_OK) return rc;
+    rc = cwq_group(b->kl, n, segments, h_segments, n_segments, b->starts, b->group_seed, b->gid, b->seg_group_off,
+                   b->workspace, b->workspace_bytes, stream);
+    if (rc != CWQ_OK) return rc;
+    rc = cwq_group_totals(b->kl, b->starts, cap, ng_dev, b->total_kl, b->K, stream);
+    if (rc != CWQ_OK) return rc;
+  }
+  if (stages & CWQ_STAGE_SCORE) {
+    rc = cwq_is_encode(b->coef, b->starts, b->K, b->group_seed, cap, ng_dev, 0, cap, max_group_size, b->index, b->workspace,
+                       b->workspace_bytes, stream);
+    if (rc != CWQ_OK) return rc;
+  }
+  if (stages & CWQ_STAGE_FINISH) {
+    rc = cwq_is_decode(b->starts, b->group_seed, b->gid, b->index, n, p_loc, p_scale, b->sample, stream);
+    if (rc != CWQ_OK) return rc;
+    rc = cwq_outlier_encode(q_loc, q_scale, b->mask, n, segments, n_segments, b->sample, b->outlier_idx, b->outlier_q,
+                            b->seg_outlier_off, b->workspace, b->workspace_bytes, stream);
+    if (rc != CWQ_OK) return rc;
+    rc = cwq_elias_delta_pack(b->index, cap, ng_dev, b->bits, b->bits_capacity_bytes, b->bit_off, b->workspace,
+                              b->workspace_bytes, stream);
+    if (rc != CWQ_OK) return rc;
+  }
+  return CWQ_OK;
+}
+
 extern "C" int cwq_fixed_pack(const uint32_t* index, int64_t count, int32_t bits_per_index, uint8_t* bits,
                               size_t bits_capacity_bytes, void* stream) {
   CWQ_REQUIRE(count > 0 && bits_per_index >= 1 && bits_per_index <= 32, "bad sizes");

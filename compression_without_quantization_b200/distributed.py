@@ -104,7 +104,8 @@ class ISShard:
     def run_planned(self, job, bounds):
         world, rank = self._world_rank()
         job.encode(bounds[rank], bounds[rank + 1])
-        job.index = all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, self.group).contiguous()
+        # in place: the finishing stages of a fused job read job.index through the raw pointer taken at allocation
+        job.index.copy_(all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, self.group))
         job.shard_bounds = bounds
 
     def plan_async(self, job, side):

@@ -8,6 +8,7 @@ the reference's grouped functions:
     greedy sampler     (CGS:170-296)   prologue -> group -> encode -> unrescale -> pack
 """
 import ctypes
+import functools
 from dataclasses import dataclass
 
 import numpy as np
@@ -95,6 +96,7 @@ def concat_to_device(arrays, device=None, what="array"):
     return parts[0] if len(parts) == 1 else torch.cat(parts)
 
 
+@functools.lru_cache(maxsize=256)
 def size_limit(max_group_size_bits, strict):
     """Running group size at which the reference's size test fires: CIS:185-187 evaluates
     ``np.log(size + 1) / np.log(2) > max_group_size_bits`` (CGS:230-232: ``>=``); the same expression is
@@ -310,6 +312,50 @@ class ISJob:
 
     def _ng_dev(self):
         return ctypes.c_void_p(0) if self.groups.synced else _ptr(self.groups.n_groups_dev)
+
+    # ---- the same stages through ONE C call (cwq_is_encode_pipeline) ----
+    def _alloc_buffers(self):
+        """Every output and the shared scratch of cwq_is_encode_pipeline.  One tensor per array on purpose: a single
+        ~80 B/dim arena was measured to make torch's caching allocator split and re-allocate its large blocks every few
+        steps (sporadic +10 ms on a 113 ms step); same-sized small blocks recycle cleanly."""
+        n, ns = self.n, self.table.count
+        cap = n + ns
+        bits_cap = ((cap * 42 + 31) // 32) * 4
+        wsb = _lib.load().cwq_is_pipeline_workspace_bytes(n, ns)
+        f32, i32, i64, u8, i16 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.int16
+        layout = [("kl", f32, n), ("coef", f32, 2 * n), ("mask", u8, n), ("gid", i32, n), ("sample", f32, n),
+                  ("outlier_idx", i64, n), ("outlier_q", i16, n), ("starts", i64, cap + 1), ("group_seed", i32, cap),
+                  ("total_kl", f32, cap), ("K", i32, cap), ("index", i32, cap), ("bit_off", i64, cap + 1),
+                  ("seg_group_off", i64, ns + 1), ("seg_outlier_off", i64, ns + 1), ("bits", u8, bits_cap), ("workspace", u8, wsb)]
+        views = {name: torch.empty(max(count, 1), dtype=dt, device=self.dev) for name, dt, count in layout}
+        self._storage = views          # keeps the scratch alive as long as the job
+        buf = _lib.ISBuffers()
+        for name in views:
+            setattr(buf, name, views[name].data_ptr())
+        buf.bits_capacity_bytes = bits_cap
+        buf.workspace_bytes = wsb
+        self._buffers = buf
+        for name in ("kl", "coef", "mask", "total_kl", "K", "index", "sample", "outlier_idx", "outlier_q", "seg_outlier_off",
+                     "bits", "bit_off"):
+            setattr(self, name, views[name])
+        self.groups = _Groups(views["starts"], views["group_seed"], views["gid"], views["seg_group_off"], None, capacity=cap)
+        self._cap = cap
+
+    def launch(self, stages):
+        """Enqueue the requested stages (bit set of _lib.STAGE_GROUP / STAGE_SCORE / STAGE_FINISH) with one call into
+        the library; the group count stays on the device.  Results are the same tensors the stage-by-stage methods
+        produce (prepare / encode / decode / pack), with capacity N + n_segments until sync_groups() trims them."""
+        if self.forced_starts is not None:
+            raise CwqError("launch() runs the grouping itself; use prepare()/encode()/decode() with forced group starts")
+        if self.n > ASYNC_MAX_DIMS:
+            raise CwqError("launch() keeps capacity-sized group tables; above {} dims use the stage methods".format(ASYNC_MAX_DIMS))
+        if not hasattr(self, "_buffers"):
+            self._alloc_buffers()
+        t = self.table
+        _lib.call("cwq_is_encode_pipeline", _ptr(self.q_loc), _ptr(self.q_scale), _ptr(self.p_loc), _ptr(self.p_scale), self.n,
+                  _ptr(t.dev), ctypes.cast(t.host, ctypes.c_void_p), t.count, max(t.max_size_limit, 1), int(stages),
+                  ctypes.cast(ctypes.pointer(self._buffers), ctypes.c_void_p), _stream())
+        return self
 
     def sync_groups(self):
         """Make the group count known on the host (one device->host copy) and trim the per-group arrays."""

@@ -127,6 +127,42 @@ CWQ_API int cwq_outlier_encode(const float* q_loc, const float* q_scale, const u
 CWQ_API int cwq_outlier_decode(float* sample, const int64_t* outlier_pos, const uint16_t* outlier_q, int64_t m,
                        void* stream);
 
+/* ---- the grouped importance-sampler encode (CIS:112-274) as ONE call -----------------------------
+ * Runs the stages above in order on `stream` with no host synchronisation and nothing between the launches
+ * but this function (the Python layer spends ~0.5 ms per call sequencing them one by one): GROUP = prologue +
+ * grouping + candidate counts, SCORE = cwq_is_encode over all groups, FINISH = decode + outliers + Elias-delta
+ * packing.  Any subset of stages may be requested (a sharded run calls GROUP, scores its own range with
+ * cwq_is_encode, all-gathers, then calls FINISH).  The group count stays on the device at
+ * seg_group_off[n_segments]; every per-group array has capacity n + n_segments (starts and bit_off one more). */
+#define CWQ_STAGE_GROUP 1
+#define CWQ_STAGE_SCORE 2
+#define CWQ_STAGE_FINISH 4
+typedef struct cwq_is_buffers {
+  float* kl;                /* [n]      */
+  float* coef;              /* [2n]     */
+  uint8_t* mask;            /* [n]      */
+  int32_t* gid;             /* [n]      */
+  float* sample;            /* [n]      */
+  int64_t* outlier_idx;     /* [n]      */
+  uint16_t* outlier_q;      /* [n]      */
+  int64_t* starts;          /* [n + n_segments + 1] */
+  uint32_t* group_seed;     /* [n + n_segments]     */
+  float* total_kl;          /* [n + n_segments]     */
+  int32_t* K;               /* [n + n_segments]     */
+  uint32_t* index;          /* [n + n_segments]     */
+  int64_t* bit_off;         /* [n + n_segments + 1] */
+  int64_t* seg_group_off;   /* [n_segments + 1]     */
+  int64_t* seg_outlier_off; /* [n_segments + 1]     */
+  uint8_t* bits;            /* bits_capacity_bytes: a multiple of 4, >= 42 bits per group of capacity */
+  size_t bits_capacity_bytes;
+  void* workspace;          /* cwq_is_pipeline_workspace_bytes(n, n_segments), shared by the stages */
+  size_t workspace_bytes;
+} cwq_is_buffers;
+CWQ_API size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments);
+CWQ_API int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale,
+                           int64_t n, const cwq_segment* segments, const cwq_segment* h_segments, int32_t n_segments,
+                           int64_t max_group_size, int32_t stages, const cwq_is_buffers* h_buffers, void* stream);
+
 /* ---- greedy sampler --------------------------------------------------------------------------
  * CGS:38-78 for groups [g0, g1): n_steps sequential steps of 2^n_bits_per_step candidates each.
  * mode 1: one persistent CTA per group, step state on chip (many groups); mode 2: all groups in lockstep,

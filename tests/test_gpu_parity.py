@@ -217,6 +217,32 @@ def test_is_batch_equals_separate_calls(cwq, syn):
         assert np.array_equal(batch[i][3][0], one[3][0]) and np.array_equal(batch[i][3][1], one[3][1])
 
 
+def test_fused_pipeline_call_equals_stage_by_stage(cwq, syn):
+    """cwq_is_encode_pipeline (one C call, group count on the device) against the same stages
+    called one by one with the host-side group count."""
+    import torch
+    from compression_without_quantization_b200 import _lib as L, engine as E
+    sizes, mg = [5000, 1, 777, 2304], [4, 4, 3, 2]
+    data = [syn.synthetic_posterior(n, 90 + i, i % 2 == 0) for i, n in enumerate(sizes)]
+    dev = E.cuda_device()
+    t = [torch.from_numpy(np.concatenate([d[j] for d in data])).to(dev) for j in range(4)]
+    specs = [E.SegmentSpec(sizes[i], 42 + i, 14, mg[i], 11, True) for i in range(len(sizes))]
+    a = E.ISJob(*t, specs).prepare(sync=True).encode().decode().pack().sync_groups()
+    b = E.ISJob(*t, specs).launch(L.STAGE_GROUP | L.STAGE_SCORE | L.STAGE_FINISH).sync_groups()
+    c = E.ISJob(*t, specs).launch(L.STAGE_GROUP)
+    c.launch(L.STAGE_SCORE).launch(L.STAGE_FINISH).sync_groups()
+    ng = a.groups.n_groups
+    for other in (b, c):
+        assert other.groups.n_groups == ng
+        for name in ("kl", "coef", "mask", "total_kl", "K", "index", "sample", "seg_outlier_off", "bit_off"):
+            assert torch.equal(getattr(a, name), getattr(other, name)), name
+        assert torch.equal(a.groups.starts, other.groups.starts) and torch.equal(a.groups.gid, other.groups.gid)
+        assert torch.equal(a.groups.group_seed, other.groups.group_seed)
+        n_out, n_bytes = int(a.seg_outlier_off[-1]), (int(a.bit_off[-1]) + 7) // 8
+        assert torch.equal(a.outlier_idx[:n_out], other.outlier_idx[:n_out]) and torch.equal(a.outlier_q[:n_out], other.outlier_q[:n_out])
+        assert torch.equal(a.bits[:n_bytes], other.bits[:n_bytes])
+
+
 def test_is_pipelined_batch_equals_single_pass(cwq, syn, monkeypatch):
     """Large batches are cut into chunks of whole calls that overlap copies, kernels and host formatting
     (coded_importance_sampler._encode_batch_pipelined); the results must not depend on the cut."""
