@@ -61,6 +61,9 @@ SIGNATURES = {
     "cwq_group_totals": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "cwq_is_encode_workspace_bytes": (_SZ, [_I64]),
     "cwq_is_encode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _SZ, _P]),
+    "cwq_is_encode_device_range": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
+    "cwq_shard_ranges_workspace_bytes": (_SZ, [_I64]),
+    "cwq_is_shard_ranges": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _SZ, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "cwq_is_pipeline_workspace_bytes": (_SZ, [_I64, _I32]),
     "cwq_is_encode_pipeline": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I32, _I64, _I32, _P, _P]),

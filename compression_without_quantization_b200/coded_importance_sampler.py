@@ -244,7 +244,10 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         if shard is None:
             job.launch(L.STAGE_SCORE | L.STAGE_FINISH)       # group count stays on the device: nothing waits for the host
         else:
-            shard.run_planned(job, shard.finish_plan(job))   # waits for the grouping of THIS chunk only
+            shard.score_async(job)                           # this rank's range, read from the device-side cuts
+            if i + 1 < n:
+                group(i + 1)                                 # queued behind the scoring, ahead of the all-gather
+            shard.gather(job)                                # host wait: the copy made right after THIS chunk's grouping
             job.launch(L.STAGE_FINISH)
         done[i] = torch.cuda.Event()
         done[i].record(compute)
@@ -265,12 +268,10 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         for i in range(n):
             collect(i)
     else:
-        # the grouping of chunk i+1 is queued BEFORE the scoring of chunk i, so that the host can read its group
-        # counts (needed for the ranges and the all-gather sizes) while chunk i is being scored
+        # sizes of the all-gather are the one thing the host must know: they arrive on the side stream while the
+        # chunk is being scored, and the download + formatting of chunk i-1 overlaps the scoring of chunk i
         group(0)
         for i in range(n):
-            if i + 1 < n:
-                group(i + 1)
             score(i)
             if i >= 1:
                 collect(i - 1)

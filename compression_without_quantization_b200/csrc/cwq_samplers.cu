@@ -26,29 +26,70 @@ constexpr int IS_WARPS = IS_THREADS / 32;
 constexpr int UNIT_CAND = 1024;  // candidates per unit
 constexpr int UNIT_BATCH = 4;    // units claimed per atomic
 
-// ng_dev (optional): the group count lives on the device and `ng` passed by the host is only a capacity
+// The scored range of groups is [g0, g1).  Either end may live on the device (g0_dev / g1_dev non-null): g1_dev is the
+// group count of a synchronisation-free encode, (g0_dev, g1_dev) the range a rank computed for itself on the device;
+// the host-side values are then only capacities and every scan runs over the capacity.
+struct GroupRange {
+  long long g0, g1;
+  const long long* g0_dev;
+  const long long* g1_dev;
+  __device__ long long begin() const { return g0_dev ? *g0_dev : g0; }
+  __device__ long long end() const { return g1_dev ? *g1_dev : g1; }
+};
 struct UnitCount {
   const int* K;
-  long long g0;
-  const long long* ng_dev;
+  GroupRange r;
   __device__ ull operator()(long long j) const {
-    if (ng_dev && j >= *ng_dev) return 0ull;
-    return (ull)((K[g0 + j] + UNIT_CAND - 1) / UNIT_CAND);
+    const long long g = r.begin() + j;
+    if (g >= r.end()) return 0ull;
+    return (ull)((K[g] + UNIT_CAND - 1) / UNIT_CAND);
   }
 };
 struct UnitDeliver {
   ull* unit_off;
   ull* keys;
-  long long g0;
-  const long long* ng_dev;
+  GroupRange r;
   __device__ void operator()(long long j, ull pre, ull) const {
-    if (ng_dev && j >= *ng_dev) return;
+    const long long g = r.begin() + j;
+    if (g >= r.end()) return;
     unit_off[j] = pre;
-    keys[g0 + j] = KEY_INIT;
+    keys[g] = KEY_INIT;
   }
 };
-__global__ void k_units_finish(ull* unit_off, long long ng, const long long* ng_dev, const ull* total, ull* counter) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { unit_off[ng_dev ? *ng_dev : ng] = *total; *counter = 0; }
+__global__ void k_units_finish(ull* unit_off, GroupRange r, const ull* total, ull* counter) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { unit_off[r.end() - r.begin()] = *total; *counter = 0; }
+}
+
+// ---- contiguous equal-work ranges of groups for the ranks of a sharded run, computed on the device ----
+// work of a group = candidates x Philox blocks per candidate; cut r (1 <= r < world) closes range r-1 behind the first
+// group whose inclusive work prefix reaches r/world of the total (integer arithmetic: every rank gets the same cuts).
+struct ShardWork {
+  const int* K;
+  const long long* starts;
+  const long long* ng_dev;
+  __device__ ull operator()(long long j) const {
+    if (j >= *ng_dev) return 0ull;
+    const int nq = (int)((starts[j + 1] - starts[j] + 3) >> 2);
+    const int blocks = row_blocks(nq);
+    return (ull)K[j] * (ull)(blocks > 0 ? blocks : 1);
+  }
+};
+struct ShardCuts {
+  const ull* total;
+  int world;
+  long long* bounds;
+  __device__ void operator()(long long j, ull pre, ull cnt) const {
+    if (cnt == 0ull) return;
+    const ull tot = *total;
+    for (int r = 1; r < world; ++r) {
+      const ull target = tot * (ull)r;
+      if (pre * (ull)world < target && (pre + cnt) * (ull)world >= target) bounds[r] = j + 1;
+    }
+  }
+};
+__global__ void k_shard_bounds_init(long long* bounds, int world, const long long* ng_dev) {
+  const int r = threadIdx.x;
+  if (r <= world) bounds[r] = r == 0 ? 0 : *ng_dev;
 }
 
 __device__ __forceinline__ ull warp_max_key(ull key) {
@@ -132,13 +173,12 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 template <bool SMALL>
 __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
-                                                         long long g0, long long ng, const long long* __restrict__ ng_dev,
-                                                         const ull* __restrict__ unit_off,
+                                                         GroupRange range, const ull* __restrict__ unit_off,
                                                          ull* __restrict__ counter, ull* __restrict__ keys) {
   __shared__ float4 s_coef[IS_WARPS][SMALL ? 8 : 32];   // 16 or 64 (a, b) pairs per warp
   __shared__ uint4 s_quad[IS_WARPS][SMALL ? 1 : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (ng_dev) ng = *ng_dev;
+  const long long g0 = range.begin(), ng = range.end() - g0;
   const ull n_units = unit_off[ng];
   float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
   for (;;) {
@@ -201,11 +241,9 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, long long g0, long long g1,
-                                                  const long long* __restrict__ ng_dev, uint32_t* __restrict__ index) {
-  long long g = g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ng_dev) g1 = *ng_dev;
-  if (g < g1) index[g] = key_index(keys[g]);
+__global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, GroupRange range, uint32_t* __restrict__ index) {
+  const long long g = range.begin() + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < range.end()) index[g] = key_index(keys[g]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -694,6 +732,42 @@ extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
   return b + 1024;
 }
 
+// groups [g0, g1) of arrays holding n_groups entries; range ends on the device where given (see GroupRange)
+static int is_encode_impl(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed, int64_t n_groups,
+                          GroupRange range, int64_t max_group_size, uint32_t* index, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc = ensure_device_props();
+  if (rc != CWQ_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // scans and the index kernel cover the host-known length of the range, or the whole capacity when an end is on the device
+  const long long span = (range.g0_dev || range.g1_dev) ? n_groups : range.g1 - range.g0;
+  Workspace ws(workspace, workspace_bytes);
+  ull* unit_off = ws.take<ull>((size_t)span + 1);
+  ull* keys = ws.take<ull>((size_t)n_groups);
+  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(span));
+  ull* total = ws.take<ull>(1);
+  ull* counter = ws.take<ull>(1);
+  if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
+  UnitCount in{K, range};
+  UnitDeliver out{unit_off, keys, range};
+  CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, span, tile_sums, total, st)));
+  k_units_finish<<<1, 32, 0, st>>>(unit_off, range, total, counter);
+  CWQ_LAUNCH_CHECK();
+  const bool prof = g_profile && g_profile_count < PROFILE_RING;
+  if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
+  if (max_group_size <= 16)
+    k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
+                                                                              group_seed, range, unit_off, counter, keys);
+  else
+    k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
+                                                                                   group_seed, range, unit_off, counter, keys);
+  CWQ_LAUNCH_CHECK();
+  if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
+  k_is_index<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(keys, range, index);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
 extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
                              int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, int64_t max_group_size,
                              uint32_t* index, void* workspace, size_t workspace_bytes, void* stream) {
@@ -701,35 +775,37 @@ extern "C" int cwq_is_encode(const float* coef, const int64_t* starts, const int
   CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
   CWQ_REQUIRE(!n_groups_dev || (g0 == 0 && g1 == n_groups), "a device-side group count needs the full range [0, capacity)");
   if (g0 == g1) return CWQ_OK;
-  int rc = ensure_device_props();
-  if (rc != CWQ_OK) return rc;
+  GroupRange range{g0, g1, nullptr, (const long long*)n_groups_dev};
+  return is_encode_impl(coef, starts, K, group_seed, n_groups, range, max_group_size, index, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cwq_is_encode_device_range(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
+                                          int64_t n_groups, const int64_t* range_dev, int64_t max_group_size, uint32_t* index,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  CWQ_REQUIRE(max_group_size >= 0, "max_group_size must be an upper bound of the group sizes");
+  CWQ_REQUIRE(n_groups > 0 && range_dev, "bad arguments");
+  GroupRange range{0, n_groups, (const long long*)range_dev, (const long long*)range_dev + 1};
+  return is_encode_impl(coef, starts, K, group_seed, n_groups, range, max_group_size, index, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t cwq_shard_ranges_workspace_bytes(int64_t n_groups) {
+  if (n_groups <= 0) return 0;
+  return align_up((size_t)scan_tiles(n_groups) * sizeof(ull)) + align_up(sizeof(ull)) + 256;
+}
+
+extern "C" int cwq_is_shard_ranges(const int32_t* K, const int64_t* starts, int64_t n_groups, const int64_t* n_groups_dev,
+                                   int32_t world, int64_t* bounds, void* workspace, size_t workspace_bytes, void* stream) {
+  CWQ_REQUIRE(K && starts && n_groups_dev && bounds && n_groups > 0 && world >= 1 && world <= 1024, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long ng = g1 - g0;
   Workspace ws(workspace, workspace_bytes);
-  ull* unit_off = ws.take<ull>((size_t)ng + 1);
-  ull* keys = ws.take<ull>((size_t)n_groups);
-  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(ng));
+  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(n_groups));
   ull* total = ws.take<ull>(1);
-  ull* counter = ws.take<ull>(1);
-  if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
-  const long long* ngd = (const long long*)n_groups_dev;
-  UnitCount in{K, g0, ngd};
-  UnitDeliver out{unit_off, keys, g0, ngd};
-  CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, ng, tile_sums, total, st)));
-  k_units_finish<<<1, 32, 0, st>>>(unit_off, ng, ngd, total, counter);
+  if (!tile_sums || !total) { set_error("cwq_is_shard_ranges: workspace too small"); return CWQ_ERR_WORKSPACE; }
+  k_shard_bounds_init<<<1, 1024, 0, st>>>((long long*)bounds, world, (const long long*)n_groups_dev);
   CWQ_LAUNCH_CHECK();
-  const bool prof = g_profile && g_profile_count < PROFILE_RING;
-  if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
-  if (max_group_size <= 16)
-    k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                              group_seed, g0, ng, ngd, unit_off, counter, keys);
-  else
-    k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                                   group_seed, g0, ng, ngd, unit_off, counter, keys);
-  CWQ_LAUNCH_CHECK();
-  if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
-  k_is_index<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(keys, g0, g1, ngd, index);
-  CWQ_LAUNCH_CHECK();
+  ShardWork in{K, (const long long*)starts, (const long long*)n_groups_dev};
+  ShardCuts out{total, world, (long long*)bounds};
+  CWQ_CUDA((device_exclusive_scan<ull, ShardWork, ShardCuts>(in, out, n_groups, tile_sums, total, st)));
   return CWQ_OK;
 }
 

@@ -76,10 +76,12 @@ class ISShard:
     """Sharded encode stage of the importance sampler: this rank scores one contiguous, work-balanced range of groups and
     one all-gather gives every rank all indices.
 
-    Called as `shard(job)` it needs the group tables on the host (one synchronisation after grouping).  The batch
-    pipeline uses the split form instead: `plan_async(job, side)` queues the range computation behind the grouping
-    and copies (cuts, group count, per-call group offsets) to the host on `side`, so the host learns them while the
-    PREVIOUS chunk is still being scored; `finish_plan(job)` then waits for that copy only."""
+    On CUDA the GPU never waits for the host: `plan_async(job, side)` computes the range cuts on the device behind the
+    grouping and starts the copy of (cuts, group count, per-call group offsets) to the host on `side`;
+    `score_async(job)` scores this rank's range straight from the device-side cuts; `gather(job)` waits for the copy --
+    which arrives while the scoring kernel runs -- because the all-gather needs its sizes on the host.
+    `shard(job)` runs the three in order.  Jobs whose group tables are already on the host (and the CPU stand-ins of the
+    gloo tests) take the plain path: ranges from the host-side tables, then the same encode and all-gather."""
 
     def __init__(self, group=None):
         self.group = group
@@ -93,17 +95,16 @@ class ISShard:
         world, rank = self._world_rank()
         g = job.groups
         if hasattr(g, "synced") and not g.synced and job.K.is_cuda:
-            # group tables still device-only (prepare(sync=False)): ranges, group count and per-call offsets come
-            # over in ONE copy, i.e. one host synchronisation per step instead of two
             self.plan_async(job, torch.cuda.current_stream())
-            bounds = self.finish_plan(job)
+            self.score_async(job)
+            self.gather(job)
         else:
             bounds = balanced_ranges(is_work(job), world)
-        self.run_planned(job, bounds)
+            job.encode(bounds[rank], bounds[rank + 1])
+            self._all_gather(job, bounds)
 
-    def run_planned(self, job, bounds):
-        world, rank = self._world_rank()
-        job.encode(bounds[rank], bounds[rank + 1])
+    def _all_gather(self, job, bounds):
+        _, rank = self._world_rank()
         # in place: the finishing stages of a fused job read job.index through the raw pointer taken at allocation
         job.index.copy_(all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, self.group))
         job.shard_bounds = bounds
@@ -111,15 +112,8 @@ class ISShard:
     def plan_async(self, job, side):
         world, _ = self._world_rank()
         g = job.groups
-        cap = int(job.K.numel())
-        ngd = g.n_groups_dev
-        sizes = g.starts[1:cap + 1] - g.starts[:cap]
-        work = job.K.to(torch.int64) * torch.clamp(row_blocks(sizes), min=1)
-        work = torch.where(torch.arange(cap, device=work.device) < ngd, work, torch.zeros_like(work))
-        parts = [ngd.to(torch.int64), g.seg_group_off.to(torch.int64)]
-        if world > 1:
-            parts.insert(0, torch.minimum(_cuts_on_device(work, world), ngd))
-        info = torch.cat(parts)
+        job._bounds_dev = job.shard_ranges_device(world)                     # world + 1 entries, computed on the device
+        info = torch.cat([job._bounds_dev, g.seg_group_off.to(torch.int64)])
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         host = torch.empty(info.shape, dtype=info.dtype, device="cpu", pin_memory=True)
@@ -131,14 +125,21 @@ class ISShard:
         info.record_stream(side)
         job._plan = (host, copied, world)
 
+    def score_async(self, job):
+        _, rank = self._world_rank()
+        job.encode_device_range(job._bounds_dev[rank:rank + 2])
+
     def finish_plan(self, job):
+        """Wait for the copy started by plan_async; installs the host-side group tables and returns the bounds."""
         host, copied, world = job._plan
         copied.synchronize()
         v = host.numpy()
-        ng = int(v[world - 1])
-        job.groups.set_host(v[world:].copy())
+        job.groups.set_host(v[world + 1:].copy())
         job.sync_groups()
-        return _bounds_from_cuts(v[:world - 1].tolist(), ng, world)
+        return [int(x) for x in v[:world + 1]]
+
+    def gather(self, job):
+        self._all_gather(job, self.finish_plan(job))
 
 
 def make_is_shard(group=None):

@@ -387,6 +387,30 @@ class ISJob:
                   cap, self._ng_dev(), g0, g1, max_size, _ptr(self.index), _ptr(ws), wsb, _stream())
         return self
 
+    def shard_ranges_device(self, world):
+        """int64[world + 1] on the device: contiguous work-balanced ranges of groups, one per rank (cwq_is_shard_ranges)."""
+        cap = int(self.K.numel())
+        bounds = torch.empty(world + 1, dtype=torch.int64, device=self.dev)
+        wsb = _lib.load().cwq_shard_ranges_workspace_bytes(cap)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        _lib.call("cwq_is_shard_ranges", _ptr(self.K), _ptr(self.groups.starts), cap, _ptr(self.groups.n_groups_dev), int(world),
+                  _ptr(bounds), _ptr(ws), wsb, _stream())
+        return bounds
+
+    def encode_device_range(self, range_dev):
+        """Score groups [range_dev[0], range_dev[1]) -- two int64 on the device -- without the host knowing the range
+        (sharded runs: the rank's range is computed behind the grouping and scoring starts at once)."""
+        cap = int(self.K.numel())
+        wsb = _lib.load().cwq_is_encode_workspace_bytes(cap)
+        if hasattr(self, "_buffers") and self._buffers.workspace_bytes >= wsb:
+            ws_ptr, wsb = ctypes.c_void_p(self._buffers.workspace), self._buffers.workspace_bytes
+        else:
+            self._range_ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+            ws_ptr = _ptr(self._range_ws)
+        _lib.call("cwq_is_encode_device_range", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
+                  cap, _ptr(range_dev), max(self.table.max_size_limit, 1), _ptr(self.index), ws_ptr, wsb, _stream())
+        return self
+
     def decode(self):
         """Regenerate the chosen rows (un-rescaled) and overwrite outlier dims; fills the side information."""
         n, t, g = self.n, self.table, self.groups

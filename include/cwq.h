@@ -109,6 +109,19 @@ CWQ_API size_t cwq_is_encode_workspace_bytes(int64_t n_groups);
 CWQ_API int cwq_is_encode(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
                   int64_t n_groups, const int64_t* n_groups_dev, int64_t g0, int64_t g1, int64_t max_group_size,
                   uint32_t* index, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for the range [range_dev[0], range_dev[1]) read on the DEVICE (two int64): a rank of a sharded run
+ * computes its own range behind the grouping and starts scoring without telling the host first.  n_groups is the
+ * capacity of the arrays; the workspace is the one of cwq_is_encode_workspace_bytes(n_groups). */
+CWQ_API int cwq_is_encode_device_range(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed,
+                               int64_t n_groups, const int64_t* range_dev, int64_t max_group_size, uint32_t* index,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* Ranges of groups for the `world` ranks of a sharded run (groups are independent: CIS:233-245): bounds[world + 1],
+ * ascending, bounds[0] = 0, bounds[world] = group count; rank r scores [bounds[r], bounds[r+1]).  Contiguous and
+ * balanced on candidates x Philox blocks per candidate.  Computed on the device from the device-side group count, so
+ * that cwq_is_encode_device_range(..., bounds + rank, ...) can follow without a host synchronisation. */
+CWQ_API size_t cwq_shard_ranges_workspace_bytes(int64_t n_groups);
+CWQ_API int cwq_is_shard_ranges(const int32_t* K, const int64_t* starts, int64_t n_groups, const int64_t* n_groups_dev,
+                        int32_t world, int64_t* bounds, void* workspace, size_t workspace_bytes, void* stream);
 /* CIS:104-109 + CIS:265/347: regenerate row index[g] of every group and un-rescale:
  * sample[i] = p_scale[i] * z + p_loc[i]. */
 CWQ_API int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,

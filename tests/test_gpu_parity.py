@@ -243,6 +243,32 @@ def test_fused_pipeline_call_equals_stage_by_stage(cwq, syn):
         assert torch.equal(a.bits[:n_bytes], other.bits[:n_bytes])
 
 
+def test_shard_ranges_on_device(cwq, syn):
+    """cwq_is_shard_ranges: contiguous ranges, every rank within one group's work of an equal share, and the
+    device-range scoring entry point gives the indices of the host-range one."""
+    import torch
+    from compression_without_quantization_b200 import _lib as L, distributed as D, engine as E
+    sizes, mg = [30000, 2304, 1], [4, 2, 4]
+    data = [syn.synthetic_posterior(n, 130 + i, False) for i, n in enumerate(sizes)]
+    dev = E.cuda_device()
+    t = [torch.from_numpy(np.concatenate([d[j] for d in data])).to(dev) for j in range(4)]
+    specs = [E.SegmentSpec(sizes[i], 42, 12, mg[i], 10, True) for i in range(len(sizes))]
+    ref = E.ISJob(*t, specs).launch(L.STAGE_GROUP | L.STAGE_SCORE).sync_groups()
+    ng = ref.groups.n_groups
+    work = D.is_work(ref).cpu().numpy().astype(np.float64)
+    for world in (1, 2, 3, 8):
+        job = E.ISJob(*t, specs).launch(L.STAGE_GROUP)
+        bounds_dev = job.shard_ranges_device(world)
+        b = bounds_dev.cpu().numpy()
+        assert b[0] == 0 and b[-1] == ng and np.all(np.diff(b) >= 0)
+        shares = np.array([work[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert np.all(np.abs(shares - work.sum() / world) <= work.max() + 1e-9)
+        assert list(b) == D.balanced_ranges(work, world)
+        for r in range(world):      # every rank's range through the device-range entry point
+            job.encode_device_range(bounds_dev[r:r + 2])
+        assert torch.equal(job.index[:ng], ref.index[:ng])
+
+
 def test_is_pipelined_batch_equals_single_pass(cwq, syn, monkeypatch):
     """Large batches are cut into chunks of whole calls that overlap copies, kernels and host formatting
     (coded_importance_sampler._encode_batch_pipelined); the results must not depend on the cut."""
