@@ -221,12 +221,16 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
     up, down = _copy_streams(dev)
     up.wait_stream(compute)
     staged = []
-    with torch.cuda.stream(up):                      # stage 1: every chunk's inputs, in order, on the copy stream
-        for a, b in chunks:
+
+    def upload(i):                                   # stage 1: a chunk's inputs on the copy stream
+        a, b = chunks[i]
+        with torch.cuda.stream(up):
             tensors = _upload(targets[a:b], proposals[a:b], dev)
             ev = torch.cuda.Event()
             ev.record(up)
-            staged.append((tensors, ev))
+        staged.append((tensors, ev))
+
+    upload(0)                                        # the other uploads are queued once chunk 0 is on its way (below)
     n = len(chunks)
     jobs, done, results = [None] * n, [None] * n, [None] * n
 
@@ -239,16 +243,16 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         if shard is not None:
             shard.plan_async(jobs[i], down)
 
-    def score(i):                                    # stage 2b: scoring (+ all-gather), decode, packing
-        job = jobs[i]
+    def score(i):                                    # stage 2b: scoring; the group count / the rank's range stay on the device
         if shard is None:
-            job.launch(L.STAGE_SCORE | L.STAGE_FINISH)       # group count stays on the device: nothing waits for the host
+            jobs[i].launch(L.STAGE_SCORE)
         else:
-            shard.score_async(job)                           # this rank's range, read from the device-side cuts
-            if i + 1 < n:
-                group(i + 1)                                 # queued behind the scoring, ahead of the all-gather
-            shard.gather(job)                                # host wait: the copy made right after THIS chunk's grouping
-            job.launch(L.STAGE_FINISH)
+            shard.score_async(jobs[i])
+
+    def finish(i):                                   # stage 2c: (all-gather,) decode, outliers, packing
+        if shard is not None:
+            shard.gather(jobs[i])                    # host wait: the copy made right after THIS chunk's grouping
+        jobs[i].launch(L.STAGE_FINISH)
         done[i] = torch.cuda.Event()
         done[i].record(compute)
 
@@ -261,21 +265,24 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         results[i] = [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
         jobs[i] = None
 
-    if shard is None:
-        for i in range(n):
-            group(i)
-            score(i)
-        for i in range(n):
-            collect(i)
-    else:
-        # sizes of the all-gather are the one thing the host must know: they arrive on the side stream while the
-        # chunk is being scored, and the download + formatting of chunk i-1 overlaps the scoring of chunk i
-        group(0)
-        for i in range(n):
-            score(i)
-            if i >= 1:
-                collect(i - 1)
-        collect(n - 1)
+    # Order on the compute stream: G0 S0 | G1 F0 S1 | G2 F1 S2 | ... : the grouping of the next chunk is queued behind the
+    # scoring of the current one and ahead of its finishing stages, so a sharded run can read the all-gather sizes of
+    # chunk i+1 (the one thing the host must know) while chunk i is being scored; download + formatting of chunk i
+    # overlap the scoring of chunk i+1.
+    group(0)
+    score(0)
+    for i in range(1, n):
+        upload(i)
+    for i in range(n):
+        if i + 1 < n:
+            group(i + 1)
+        finish(i)
+        if i + 1 < n:
+            score(i + 1)
+        if shard is not None and i >= 1:
+            collect(i - 1)
+    for i in range(0 if shard is None else max(n - 1, 0), n):
+        collect(i)
     compute.wait_stream(down)
     return [r for chunk in results for r in chunk]
 
