@@ -5,7 +5,7 @@
 // Work decomposition of the importance sampler (the dominant kernel, k_is_score):
 //   a group's K candidates are cut into UNITs of 1024; a WARP claims a short run of consecutive
 //   units from a global counter, scores 32 candidates at a time (one candidate per lane, its
-//   ceil(G/4) Philox blocks and Box-Muller pairs generated in registers, never stored), keeps a
+//   Philox blocks (3 per 16 dims) and Box-Muller pairs generated in registers, never stored), keeps a
 //   per-lane (score, index) best, shuffle-reduces it and publishes one 64-bit atomicMax per run.
 //   No __syncthreads, no HBM traffic beyond the 8 B/dim coefficients and 8 B/group keys.
 #include "cwq_common.cuh"
