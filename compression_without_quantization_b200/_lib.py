@@ -78,7 +78,7 @@ SIGNATURES = {
     "cwq_elias_delta_pack": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P, _P, _SZ, _P]),
     "cwq_fixed_pack": (ctypes.c_int, [_P, _I64, _I32, _P, _SZ, _P]),
     "cwq_fixed_unpack": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
-    "cwq_bits_to_ascii": (ctypes.c_int, [_P, _I64, _P, _P]),
+    "cwq_bits_to_ascii": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
     "cwq_elias_delta_parse_host": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "cwq_ac_encode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _P, _I64, _P]),
     "cwq_ac_decode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),

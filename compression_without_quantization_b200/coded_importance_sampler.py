@@ -159,18 +159,16 @@ def _segment_result(job, s, host, return_indices):
 def _host_views(job, with_bits):
     """One batch of device->host copies for everything the caller gets back."""
     ng = job.groups.n_groups
-    if with_bits:
-        counts = torch.cat([job.seg_outlier_off[-1:], job.bit_off[ng:ng + 1]]).cpu().numpy()
-        off_tail, total_bits = int(counts[0]), int(counts[1])
-    else:
-        off_tail, total_bits = int(job.seg_outlier_off[-1:].cpu().numpy()[0]), 0
-    n_out = off_tail
+    counts = [job.seg_outlier_off[-1:]] + ([job.bit_off[ng:ng + 1]] if with_bits else [])
+    counts = [int(c[0]) for c in E.to_host(counts)]          # copies only: no kernel on this stream
+    n_out, total_bits = counts[0], (counts[1] if with_bits else 0)
     names = ["sample", "starts", "index", "outlier_idx", "outlier_q", "seg_outlier_off"]
     tensors = [job.sample, job.groups.starts, job.index, job.outlier_idx[:n_out], job.outlier_q[:n_out], job.seg_outlier_off]
     if with_bits:
         # packed bits -> the reference's '0'/'1' characters on the device, once for the whole batch
         names += ["bit_off", "ascii"]
-        tensors += [job.bit_off, E.device_bits_to_ascii(job.bits, total_bits)]
+        ascii_dev = job.ascii[:total_bits] if hasattr(job, "ascii") else E.device_bits_to_ascii(job.bits, total_bits)
+        tensors += [job.bit_off, ascii_dev]
     host = dict(zip(names, E.to_host(tensors)))
     host["index"] = host["index"].view(np.uint32)
     host["outlier_q"] = host["outlier_q"].view(np.uint16)
@@ -207,18 +205,28 @@ _side_streams = {}
 
 
 def _copy_streams(dev):
-    """One upload and one download stream per device, created once: torch's caching allocator keeps a pool per
-    stream, so fresh streams on every call would turn every buffer into a new cudaMalloc."""
+    """Upload, download and 'peek' streams of a device, created once: torch's caching allocator keeps a pool per
+    stream, so fresh streams on every call would turn every buffer into a new cudaMalloc.  The peek stream carries the
+    small copies that tell the host a chunk's group count; they wait for a grouping queued far ahead and must not sit
+    in front of the downloads of an earlier chunk."""
     key = (dev.type, dev.index)
     if key not in _side_streams:
-        _side_streams[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        _side_streams[key] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
     return _side_streams[key]
 
 
-def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, shard=None):
+def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, shard=None, trace=None):
+    """trace: optional list that receives (label, host seconds since entry) marks (tools/profile_pipeline.py)."""
+    import time
+    t_entry = time.perf_counter()
+
+    def mark(label):
+        if trace is not None:
+            trace.append((label, time.perf_counter() - t_entry))
+
     dev = E.cuda_device()
     compute = torch.cuda.current_stream()
-    up, down = _copy_streams(dev)
+    up, down, peek = _copy_streams(dev)
     up.wait_stream(compute)
     staged = []
 
@@ -240,8 +248,11 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         for t in tensors:
             t.record_stream(compute)
         jobs[i] = E.ISJob(*tensors, specs[a:b]).launch(L.STAGE_GROUP)
+        # the group count (sharded: also the ranges) starts travelling to the host on the side stream
         if shard is not None:
-            shard.plan_async(jobs[i], down)
+            shard.plan_async(jobs[i], peek)
+        else:
+            jobs[i].groups.fetch_async(peek)
 
     def score(i):                                    # stage 2b: scoring; the group count / the rank's range stay on the device
         if shard is None:
@@ -249,40 +260,50 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
         else:
             shard.score_async(jobs[i])
 
-    def finish(i):                                   # stage 2c: (all-gather,) decode, outliers, packing
+    def finish(i):                                   # stage 2c: (all-gather,) decode, outliers, packing, '0'/'1' expansion
+        job = jobs[i]
         if shard is not None:
-            shard.gather(jobs[i])                    # host wait: the copy made right after THIS chunk's grouping
-        jobs[i].launch(L.STAGE_FINISH)
+            shard.gather(job)                        # host wait: the copy made right after THIS chunk's grouping
+        else:
+            job.groups.finish_fetch()
+            job.sync_groups()
+        job.launch(L.STAGE_FINISH)
+        if not return_indices:
+            job.expand_code_async()                  # sized by the group count the host has just learnt
         done[i] = torch.cuda.Event()
         done[i].record(compute)
 
-    def collect(i):                                  # stage 3: download + formatting while later chunks are scored
+    def collect(i):                                  # stage 3: download (copies only) + formatting while later chunks are scored
         job = jobs[i]
         down.wait_event(done[i])
         with torch.cuda.stream(down):
-            job.sync_groups()
             host = _host_views(job, with_bits=not return_indices)
         results[i] = [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
         jobs[i] = None
 
     # Order on the compute stream: G0 S0 | G1 F0 S1 | G2 F1 S2 | ... : the grouping of the next chunk is queued behind the
-    # scoring of the current one and ahead of its finishing stages, so a sharded run can read the all-gather sizes of
-    # chunk i+1 (the one thing the host must know) while chunk i is being scored; download + formatting of chunk i
-    # overlap the scoring of chunk i+1.
+    # scoring of the current one and ahead of its finishing stages.  The host learns the group count of chunk i (needed to
+    # size the all-gather of a sharded run and the expanded code) from a side-stream copy made right after G(i), i.e.
+    # while chunk i-1 is still being scored, so the GPU never waits for it; download + formatting of chunk i overlap the
+    # scoring of chunk i+1 and need no kernel (a kernel would queue behind the resident scoring CTAs).
     group(0)
     score(0)
+    mark("chunk 0 queued")
     for i in range(1, n):
         upload(i)
+    mark("uploads queued")
     for i in range(n):
         if i + 1 < n:
             group(i + 1)
         finish(i)
+        mark("finish %d queued" % i)
         if i + 1 < n:
             score(i + 1)
-        if shard is not None and i >= 1:
+        if i >= 1:
             collect(i - 1)
-    for i in range(0 if shard is None else max(n - 1, 0), n):
-        collect(i)
+            mark("chunk %d collected" % (i - 1))
+    collect(n - 1)
+    mark("chunk %d collected" % (n - 1))
     compute.wait_stream(down)
     return [r for chunk in results for r in chunk]
 

@@ -609,8 +609,13 @@ __global__ void __launch_bounds__(256) k_fixed_unpack(const uint8_t* __restrict_
 
 // packed MSB-first bits -> the reference's '0'/'1' characters (what BIO:76-79 consumes), 8 characters per thread.
 // `ascii` holds 8 * ceil(n_bits / 8) bytes: the last thread may write up to 7 characters past n_bits.
-__global__ void __launch_bounds__(256) k_bits_to_ascii(const uint8_t* __restrict__ bits, long long n_bytes, uint2* __restrict__ ascii) {
+// 64-thread CTAs (18 registers per thread): one fits beside the three resident k_is_score CTAs of an SM (61 440 of
+// 65 536 registers taken), so the expansion of one chunk can run on the download stream while the next chunk is scored.
+constexpr int ASCII_THREADS = 64;
+__global__ void __launch_bounds__(ASCII_THREADS) k_bits_to_ascii(const uint8_t* __restrict__ bits, long long n_bytes,
+                                                       const long long* __restrict__ n_bits_dev, uint2* __restrict__ ascii) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_bits_dev) { const long long nb = (*n_bits_dev + 7) >> 3; n_bytes = nb < n_bytes ? nb : n_bytes; }
   if (i >= n_bytes) return;
   const uint32_t b = bits[i];
   uint32_t lo = 0x30303030u, hi = 0x30303030u;   // characters 0-3 (bits 7..4) and 4-7 (bits 3..0), little-endian words
@@ -1016,12 +1021,13 @@ extern "C" int cwq_fixed_unpack(const uint8_t* bits, int64_t count, int32_t bits
   return CWQ_OK;
 }
 
-extern "C" int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, uint8_t* ascii, void* stream) {
+extern "C" int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, const int64_t* n_bits_dev, uint8_t* ascii, void* stream) {
   CWQ_REQUIRE(n_bits >= 0 && (n_bits == 0 || (bits && ascii)), "bad arguments");
   CWQ_REQUIRE((reinterpret_cast<uintptr_t>(ascii) & 7u) == 0, "ascii must be 8-byte aligned");
   if (n_bits == 0) return CWQ_OK;
   const long long n_bytes = (n_bits + 7) / 8;
-  k_bits_to_ascii<<<(unsigned)((n_bytes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, n_bytes, reinterpret_cast<uint2*>(ascii));
+  k_bits_to_ascii<<<(unsigned)((n_bytes + ASCII_THREADS - 1) / ASCII_THREADS), ASCII_THREADS, 0, (cudaStream_t)stream>>>(bits, n_bytes, (const long long*)n_bits_dev,
+                                                                                      reinterpret_cast<uint2*>(ascii));
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }

@@ -176,6 +176,24 @@ class _Groups:
             self.set_host(self.seg_group_off.cpu().numpy())
         return self
 
+    def fetch_async(self, side):
+        """Start copying the per-segment group offsets (and with them the group count) to the host on stream `side`,
+        behind everything queued so far on the current stream; finish_fetch() waits for that copy only."""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        host = torch.empty(self.seg_group_off.shape, dtype=self.seg_group_off.dtype, device="cpu", pin_memory=True)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host.copy_(self.seg_group_off, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+        self._fetch = (host, copied)
+
+    def finish_fetch(self):
+        host, copied = self._fetch
+        copied.synchronize()
+        return self.set_host(host.numpy().copy())
+
     def set_host(self, seg_group_off_host):
         """Install the host copy of the per-segment group offsets (however it was brought over) and trim the views."""
         self.seg_group_off_host = np.asarray(seg_group_off_host, dtype=np.int64)
@@ -249,13 +267,14 @@ def bits_to_ascii(bits_host, n_bits, bit_begin=0):
     return (u[lo:lo + n_bits] + np.uint8(48)).tobytes()
 
 
-def device_bits_to_ascii(bits, n_bits):
+def device_bits_to_ascii(bits, n_bits, n_bits_dev=None):
     """Packed MSB-first bits on the device -> '0'/'1' characters on the device (uint8[n_bits]); the expansion runs at
-    HBM speed instead of costing the host an unpackbits pass per call."""
+    HBM speed instead of costing the host an unpackbits pass per call.  With n_bits_dev (int64 on the device) the
+    count is read there and n_bits is the capacity of the result."""
     n_bits = int(n_bits)
     out = torch.empty(8 * ((n_bits + 7) // 8), dtype=torch.uint8, device=bits.device)
     if n_bits:
-        _lib.call("cwq_bits_to_ascii", _ptr(bits), n_bits, _ptr(out), _stream())
+        _lib.call("cwq_bits_to_ascii", _ptr(bits), n_bits, _ptr(n_bits_dev), _ptr(out), _stream())
     return out[:n_bits]
 
 
@@ -385,6 +404,14 @@ class ISJob:
             max_size = max(int(np.diff(np.asarray(st)).max()) for st in self.forced_starts)
         _lib.call("cwq_is_encode", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
                   cap, self._ng_dev(), g0, g1, max_size, _ptr(self.index), _ptr(ws), wsb, _stream())
+        return self
+
+    def expand_code_async(self):
+        """Queue the '0'/'1' expansion of the packed code behind the packing, on the current stream, once the group count
+        is known on the host (42 bits per group bound the buffer; the bit count itself stays on the device).  Collecting
+        the results then needs copies only -- no kernel that would have to wait for SM room behind a scoring kernel."""
+        ng = self.groups.n_groups
+        self.ascii = device_bits_to_ascii(self.bits, 42 * ng, self.bit_off[ng:ng + 1])
         return self
 
     def shard_ranges_device(self, world):

@@ -206,8 +206,10 @@ CWQ_API int cwq_fixed_pack(const uint32_t* index, int64_t count, int32_t bits_pe
                    size_t bits_capacity_bytes, void* stream);
 CWQ_API int cwq_fixed_unpack(const uint8_t* bits, int64_t count, int32_t bits_per_index, uint32_t* index, void* stream);
 /* Packed MSB-first bits -> '0'/'1' characters, the form in which the reference carries every code
- * (CIS:258-260, CGS:286-287, consumed by BIO:76-79).  ascii: device buffer of 8 * ceil(n_bits / 8) bytes, 8-byte aligned. */
-CWQ_API int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, uint8_t* ascii, void* stream);
+ * (CIS:258-260, CGS:286-287, consumed by BIO:76-79).  ascii: device buffer of 8 * ceil(n_bits / 8) bytes, 8-byte
+ * aligned.  n_bits_dev (may be NULL): the number of bits is read on the device and n_bits is only the capacity
+ * (e.g. bit_off + n_groups of cwq_elias_delta_pack with 42 bits per group as the bound). */
+CWQ_API int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, const int64_t* n_bits_dev, uint8_t* ascii, void* stream);
 /* BIO:22-39 over a whole stream of n_codes codes; HOST function on a HOST '0'/'1' byte string
  * (the sequential parse the decoder does, CIS:325-336).  h_index receives x - 1. */
 CWQ_API int cwq_elias_delta_parse_host(const uint8_t* h_ascii_bits, int64_t n_bits, int64_t n_codes, uint32_t* h_index,
