@@ -11,6 +11,8 @@ B200 engine.  Names, argument order, defaults, return types and error messages f
 their arrays may be numpy, torch (CPU or CUDA) or any DLPack producer.  `sess` is accepted and ignored.
 `*_batch` variants run many reference calls in one launch sequence (same results per call).
 """
+import time
+
 import numpy as np
 import torch
 
@@ -217,7 +219,6 @@ def _copy_streams(dev):
 
 def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, shard=None, trace=None):
     """trace: optional list that receives (label, host seconds since entry) marks (tools/profile_pipeline.py)."""
-    import time
     t_entry = time.perf_counter()
 
     def mark(label):
