@@ -7,6 +7,7 @@ the reference's grouped functions:
     importance sampler (CIS:112-274)   prologue -> group -> totals -> encode -> decode -> outliers -> pack
     greedy sampler     (CGS:170-296)   prologue -> group -> encode -> unrescale -> pack
 """
+import collections
 import ctypes
 import functools
 from dataclasses import dataclass
@@ -121,6 +122,29 @@ class SegmentSpec:
     strict: bool = True  # True: importance sampler ('>'), False: greedy ('>=')
 
 
+_table_cache = collections.OrderedDict()   # (device, table bytes) -> device tensor; tables are read-only on the device
+
+
+def _segment_table_on_device(raw, device):
+    """Device copy of a segment table.  Repeated calls with the same parameters (a codec encoding image after image, a
+    benchmark loop) reuse one upload; a new table goes through pinned memory with an asynchronous copy -- a pageable
+    upload would block the host until everything already queued on the stream has run, which serialises the chunks of
+    the batch pipeline."""
+    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0, raw)
+    hit = _table_cache.get(key)
+    if hit is not None:
+        _table_cache.move_to_end(key)
+        return hit
+    staging = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    if device.type == "cuda":
+        staging = staging.pin_memory()
+    dev = staging.to(device, non_blocking=True)
+    _table_cache[key] = dev
+    while len(_table_cache) > 64:
+        _table_cache.popitem(last=False)
+    return dev
+
+
 class SegmentTable:
     def __init__(self, specs, device):
         self.specs = list(specs)
@@ -138,12 +162,7 @@ class SegmentTable:
             off += sp.n
         self.n = off
         self.starts = [int(s.start) for s in self.host]
-        # pinned staging + asynchronous copy: a pageable upload would block the host until everything already
-        # queued on the stream has run, which serialises the chunks of the batch pipeline
-        staging = torch.frombuffer(bytearray(bytes(self.host)), dtype=torch.uint8)
-        if torch.device(device).type == "cuda":
-            staging = staging.pin_memory()
-        self.dev = staging.to(device, non_blocking=True)
+        self.dev = _segment_table_on_device(bytes(self.host), torch.device(device))
         self.max_size_limit = max(int(s.size_limit) for s in self.host)
 
 
