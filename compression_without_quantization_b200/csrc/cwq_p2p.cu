@@ -108,8 +108,9 @@ extern "C" int cwq_p2p_exchange_indices(const void* score_workspace, int64_t n_g
   CWQ_LAUNCH_CHECK();
   k_p2p_signal<<<1, 32, 0, st>>>(peers, world, rank, parity, (ull)epoch);
   CWQ_LAUNCH_CHECK();
-  int clock_khz = 1965000;
-  cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0);
+  int clock_khz = 1965000, device = 0;
+  CWQ_CUDA(cudaGetDevice(&device));
+  cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device);
   const long long timeout_cycles = (long long)(timeout_seconds * 1e3 * (double)clock_khz);
   int* status = reinterpret_cast<int*>((char*)h_peer_buffers[rank] + CWQ_P2P_STATUS_OFFSET);
   k_p2p_wait<<<1, 32, 0, st>>>(reinterpret_cast<const ull*>(h_peer_buffers[rank]), world, parity, (ull)epoch, timeout_cycles, status);
