@@ -58,6 +58,20 @@ def test_normal_stream_statistics_and_addressing(oracle):
     assert not np.array_equal(oracle.default_normal_source(43, 0, 4, 16), z[:4])
 
 
+def test_harvested_quad_is_standard_normal_and_uncorrelated_with_the_direct_quads(oracle):
+    """Dims 12..15 of a unit come from the top bytes of the words whose low 23 bits give dims 0..11:
+    same distribution, no linear correlation between any two dims of a unit (nor between their squares)."""
+    z = oracle.default_normal_source(7, 0, 60000, 32).astype(np.float64)
+    for d in range(32):
+        col = z[:, d]
+        assert abs(col.mean()) < 0.02 and abs(col.std() - 1) < 0.02 and abs(np.mean(col ** 4) - 3) < 0.15
+        assert abs(np.mean(np.abs(col) < 0.6744897501960817) - 0.5) < 0.01      # quartiles of N(0,1)
+    c = np.corrcoef(z.T)
+    c2 = np.corrcoef((z ** 2).T)
+    off = ~np.eye(32, dtype=bool)
+    assert np.abs(c[off]).max() < 0.02 and np.abs(c2[off]).max() < 0.02
+
+
 def test_deterministic_log_exp_accuracy(oracle):
     rng = np.random.default_rng(0)
     xs = np.exp(rng.uniform(-30, 30, 4000)).astype(np.float32)
