@@ -180,8 +180,6 @@ def main():
     ap.add_argument("--images", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
-                    help="N > 1: how the ranks exchange the per-group indices (NVLink peer-memory stores / NCCL all-gather)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +217,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    shard_device = D.make_is_shard(p2p=args.exchange == "p2p") if world > 1 else None
+    shard_device = D.make_is_shard() if world > 1 else None
 
     def step_device():
         job = E.ISJob(devt[0], devt[1], devt[2], devt[3], specs)
@@ -287,7 +285,7 @@ def main():
         targets = [Normal(host[0][off[i]:off[i + 1]], host[1][off[i]:off[i + 1]]) for i in range(len(segs))]
         proposals = [Normal(host[2][off[i]:off[i + 1]], host[3][off[i]:off[i + 1]]) for i in range(len(segs))]
         mgs = [mg for _, mg in segs]
-        shard = D.make_is_shard(p2p=args.exchange == "p2p") if world > 1 else None
+        shard = D.make_is_shard() if world > 1 else None
 
         def step_e2e():
             return cwq.code_grouped_importance_sample_batch(targets, proposals, SEED, N_BITS_PER_GROUP, mgs,
@@ -372,7 +370,7 @@ def main():
                                "max_group_size_bits=4/2, dim_kl_bit_limit=16, seed=42 (BASELINE configs[3])".format(args.images, n1, n2),
                    "dims": n_total, "groups": n_groups, "candidates": candidates, "candidate_dims": cand_dims,
                    "parallelism": "groups sharded in {} contiguous work-balanced ranges + {} of indices".format(
-                       world, "exchange over NVLink peer memory" if args.exchange == "p2p" and world > 1 else "all-gather"),
+                       world, "all-gather"),
                    "l2": "compute-bound path: inputs are 76 MB (< L2) but are read once per step by the O(N) stages only; "
                          "every step rewrites >126 MB of scratch (next/exit/gid/starts) between reads"},
         "candidates_per_sec": candidates / s, "candidate_dims_per_sec": cand_dims / s,

@@ -36,7 +36,6 @@ class ISBuffers(ctypes.Structure):
 
 
 STAGE_GROUP, STAGE_SCORE, STAGE_FINISH = 1, 2, 4
-P2P_MAX_WORLD, P2P_HEADER_BYTES, P2P_STATUS_OFFSET = 8, 512, 256
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -65,12 +64,6 @@ SIGNATURES = {
     "cwq_is_encode_device_range": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
     "cwq_shard_ranges_workspace_bytes": (_SZ, [_I64]),
     "cwq_is_shard_ranges": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _SZ, _P]),
-    "cwq_p2p_buffer_bytes": (_SZ, [_I64]),
-    "cwq_p2p_alloc": (ctypes.c_int, [_SZ, _P, _P]),
-    "cwq_p2p_open": (ctypes.c_int, [_P, _P]),
-    "cwq_p2p_close": (ctypes.c_int, [_P]),
-    "cwq_p2p_free": (ctypes.c_int, [_P]),
-    "cwq_p2p_exchange_indices": (ctypes.c_int, [_P, _I64, _P, _P, _I32, _I32, ctypes.c_uint64, _I64, ctypes.c_double, _P, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "cwq_is_pipeline_workspace_bytes": (_SZ, [_I64, _I32]),
     "cwq_is_encode_pipeline": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I32, _I64, _I32, _P, _P]),

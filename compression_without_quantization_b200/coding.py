@@ -54,8 +54,8 @@ class ArithmeticCoder(object):
                                                 self._precision, 1 if fast else 0, self._ptr(out), int(cap),
                                                 ctypes.cast(ctypes.pointer(n), ctypes.c_void_p),
                                                 ctypes.cast(ctypes.pointer(used), ctypes.c_void_p))
-            if rc == -3 and cap < (1 << 28):   # CWQ_ERR_WORKSPACE: message longer than guessed
-                cap *= 8
+            if rc == -3 and cap < (1 << 31):   # CWQ_ERR_WORKSPACE: message longer than guessed; n holds its true length
+                cap = max(int(n.value), 2 * cap)
                 continue
             _lib.check(rc, "cwq_ac_decode_host")
             self.bits_used = int(used.value)

@@ -106,7 +106,10 @@ extern "C" int cwq_ac_decode_host(const int64_t* h_counts, int32_t n_symbols, co
     high = low + (width * m.D[j]) / m.R;
     low = low + (width * m.C[j]) / m.R;
     if (j == 0) break;   // symbol 0 ends the message (coding.pyx:180, 271)
-    AC_REQUIRE(n <= capacity + 1 && i <= n_bits + 64 * (int64_t)precision, "message longer than the output buffer or the stream");
+    // A message may hold far more symbols than the stream has bits (a skewed histogram codes a symbol in a fraction of a
+    // bit): symbols past `capacity` are counted, not stored, and the caller retries with the count (CWQ_ERR_WORKSPACE).
+    // Only the stream position bounds the loop: every symbol narrows the interval, so a corrupt stream runs out of bits.
+    AC_REQUIRE(i <= n_bits + 64 * (int64_t)precision, "corrupt stream (no end symbol within the stream)");
     while (high < half || low > half) {
       if (high < half) { low *= 2; high *= 2; z *= 2; }
       else { low = (low - half) * 2; high = (high - half) * 2; z = (z - half) * 2; }

@@ -4,9 +4,6 @@ costs, and the only data-path collective is one all-gather of the per-group indi
 NVLink when the tensors are on CUDA; gloo on CPU in the tests).  One process per GPU, torch.distributed
 for the plumbing.
 """
-import atexit
-import ctypes
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -75,91 +72,6 @@ def greedy_work(job):
     return torch.clamp(row_blocks(sizes), min=1)
 
 
-class P2PIndexExchange:
-    """The index exchange of a sharded run over NVLink peer memory (csrc/cwq_p2p.cu) instead of an all-gather: the rank
-    that found an index stores it into every rank's index array, raises a flag on every peer, and a one-block kernel
-    waits for the flags of all ranks.  Nothing of it involves the host.  One instance per process; buffers are
-    allocated (and their IPC handles exchanged, a host-side collective) on first use and when the capacity grows."""
-
-    def __init__(self, group=None, timeout_seconds=2.0):
-        self.group, self.timeout = group, float(timeout_seconds)
-        self.capacity, self.epoch = 0, 0
-        self.local, self.peers, self.opened = None, [], []
-        atexit.register(self.close)
-
-    def _world_rank(self):
-        if dist.is_initialized():
-            return dist.get_world_size(self.group), dist.get_rank(self.group)
-        return 1, 0
-
-    def ensure(self, capacity_groups):
-        """Collective: every rank calls it with the same capacity."""
-        from . import _lib
-        world, rank = self._world_rank()
-        if world > _lib.P2P_MAX_WORLD:
-            raise _lib.CwqError("peer-memory exchange supports up to {} ranks".format(_lib.P2P_MAX_WORLD))
-        if capacity_groups <= self.capacity:
-            return self
-        torch.cuda.synchronize()              # nobody may still be reading the buffers that are about to go
-        if world > 1:
-            dist.barrier(self.group)
-        self.close()
-        cap = 1 << max(int(capacity_groups - 1).bit_length(), 20)
-        nbytes = _lib.load().cwq_p2p_buffer_bytes(cap)
-        ptr, handle = ctypes.c_void_p(0), (ctypes.c_uint8 * 64)()
-        _lib.call("cwq_p2p_alloc", nbytes, ctypes.cast(ctypes.pointer(ptr), ctypes.c_void_p), ctypes.cast(handle, ctypes.c_void_p))
-        self.local, self.nbytes, self.capacity = ptr.value, nbytes, cap
-        handles = [None] * world
-        if world > 1:
-            dist.all_gather_object(handles, bytes(handle), group=self.group)
-        self.peers = []
-        for r in range(world):
-            if r == rank:
-                self.peers.append(self.local)
-                continue
-            p = ctypes.c_void_p(0)
-            h = (ctypes.c_uint8 * 64).from_buffer_copy(handles[r])
-            _lib.call("cwq_p2p_open", ctypes.cast(h, ctypes.c_void_p), ctypes.cast(ctypes.pointer(p), ctypes.c_void_p))
-            self.peers.append(p.value)
-            self.opened.append(p.value)
-        self.peer_array = (ctypes.c_void_p * world)(*self.peers)
-        self.epoch = 0
-        if world > 1:
-            dist.barrier(self.group)
-        return self
-
-    def exchange(self, job, bounds_dev):
-        """Queue publish + signal + wait + copy-out behind the job's scoring kernel; afterwards (in stream order) the
-        job's index array holds the indices of all groups."""
-        from . import _lib, engine as E
-        world, rank = self._world_rank()
-        self.epoch += 1
-        cap = job._score_cap
-        _lib.call("cwq_p2p_exchange_indices", job._score_ws, cap, E._ptr(bounds_dev[rank:rank + 2]),
-                  ctypes.cast(self.peer_array, ctypes.c_void_p), world, rank, self.epoch, self.capacity, self.timeout,
-                  E._ptr(job.index), E._stream())
-
-    def status(self):
-        """0, or 1 + the rank whose flag did not arrive within the timeout (synchronises the current stream)."""
-        from . import _lib
-        from . import engine as E
-        if not self.local:
-            return 0
-        view = E.raw_device_tensor(self.local, _lib.P2P_HEADER_BYTES, E.cuda_device())
-        return int(view[_lib.P2P_STATUS_OFFSET:_lib.P2P_STATUS_OFFSET + 4].view(torch.int32).cpu()[0])
-
-    def close(self):
-        from . import _lib
-        try:
-            for p in self.opened:
-                _lib.load().cwq_p2p_close(ctypes.c_void_p(p))
-            if self.local:
-                _lib.load().cwq_p2p_free(ctypes.c_void_p(self.local))
-        except Exception:
-            pass
-        self.opened, self.peers, self.local, self.capacity = [], [], None, 0
-
-
 class ISShard:
     """Sharded encode stage of the importance sampler: this rank scores one contiguous, work-balanced range of groups and
     one all-gather gives every rank all indices.
@@ -171,9 +83,8 @@ class ISShard:
     `shard(job)` runs the three in order.  Jobs whose group tables are already on the host (and the CPU stand-ins of the
     gloo tests) take the plain path: ranges from the host-side tables, then the same encode and all-gather."""
 
-    def __init__(self, group=None, p2p=None):
+    def __init__(self, group=None):
         self.group = group
-        self.p2p = p2p           # a P2PIndexExchange: indices travel through peer memory instead of an all-gather
 
     def _world_rank(self):
         if dist.is_initialized():
@@ -202,8 +113,6 @@ class ISShard:
         world, _ = self._world_rank()
         g = job.groups
         job._bounds_dev = job.shard_ranges_device(world)                     # world + 1 entries, computed on the device
-        if self.p2p is not None:
-            self.p2p.ensure(int(job.K.numel()))
         info = torch.cat([job._bounds_dev, g.seg_group_off.to(torch.int64)])
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
@@ -230,26 +139,13 @@ class ISShard:
         return [int(x) for x in v[:world + 1]]
 
     def gather(self, job):
-        if self.p2p is None:
-            self._all_gather(job, self.finish_plan(job))
-            return
-        # peer-memory exchange: queued at once (the GPU side needs nothing from the host); the host-side tables are
-        # installed afterwards for the caller's benefit (result sizes), then the index array is re-pointed and trimmed
-        self.p2p.exchange(job, job._bounds_dev)
-        job.shard_bounds = self.finish_plan(job)
+        self._all_gather(job, self.finish_plan(job))
 
 
-_p2p_exchanges = {}
-
-
-def make_is_shard(group=None, p2p=False):
-    """`shard` object for code_grouped_importance_sample_batch: encode this rank's range, exchange the indices
-    (p2p=False: one NCCL all-gather; p2p=True: stores into every rank's index array over NVLink peer memory)."""
-    if not p2p:
-        return ISShard(group)
-    if group not in _p2p_exchanges:
-        _p2p_exchanges[group] = P2PIndexExchange(group)
-    return ISShard(group, _p2p_exchanges[group])
+def make_is_shard(group=None):
+    """`shard` object for code_grouped_importance_sample_batch: encode this rank's range, then one NCCL all-gather of
+    the per-group indices."""
+    return ISShard(group)
 
 
 def make_greedy_shard(group=None):

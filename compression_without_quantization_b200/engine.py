@@ -22,18 +22,6 @@ from ._lib import CwqError, Segment
 # ----------------------------------------------------------------------------------------------
 # small helpers
 # ----------------------------------------------------------------------------------------------
-class _RawDeviceMemory:
-    """`__cuda_array_interface__` view of device memory that torch did not allocate (cwq_p2p_alloc / cwq_p2p_open)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-
-
-def raw_device_tensor(ptr, nbytes, device):
-    """uint8 CUDA tensor aliasing nbytes at ptr (no ownership)."""
-    return torch.as_tensor(_RawDeviceMemory(ptr, nbytes), device=device)
-
-
 def cuda_device():
     if not torch.cuda.is_available():
         raise CwqError("no CUDA device visible: the engine has no CPU fallback")
@@ -465,7 +453,6 @@ class ISJob:
         else:
             self._range_ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
             ws_ptr = _ptr(self._range_ws)
-        self._score_ws, self._score_cap = ws_ptr, cap      # the peer-memory index exchange reads the keys from here
         _lib.call("cwq_is_encode_device_range", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
                   cap, _ptr(range_dev), max(self.table.max_size_limit, 1), _ptr(self.index), ws_ptr, wsb, _stream())
         return self

@@ -122,30 +122,6 @@ CWQ_API int cwq_is_encode_device_range(const float* coef, const int64_t* starts,
 CWQ_API size_t cwq_shard_ranges_workspace_bytes(int64_t n_groups);
 CWQ_API int cwq_is_shard_ranges(const int32_t* K, const int64_t* starts, int64_t n_groups, const int64_t* n_groups_dev,
                         int32_t world, int64_t* bounds, void* workspace, size_t workspace_bytes, void* stream);
-/* ---- index exchange of a sharded run over NVLink peer memory -----------------------------------
- * Instead of a collective call after the scoring stage, the rank that found an index stores it into EVERY rank's
- * index array through peer-mapped memory and raises a flag on every peer; a one-block kernel waits for all flags
- * before the finishing stages.  No host involvement: no sizes to agree on, no collective launch.
- * Each rank owns one exchange buffer (cwq_p2p_alloc: cudaMalloc + IPC handle); the 64-byte handles are exchanged by the
- * host layer once (e.g. torch.distributed.all_gather_object) and opened with cwq_p2p_open.  Layout of a buffer:
- * [flags: 2 x CWQ_P2P_MAX_WORLD u64][status i32 at CWQ_P2P_STATUS_OFFSET] ... header of CWQ_P2P_HEADER_BYTES, then two
- * index arrays of capacity_groups u32 (256-byte aligned), used alternately by the parity of `epoch`.
- * cwq_p2p_exchange_indices: to be queued right after cwq_is_encode_device_range on the same stream with the SAME
- * workspace; publishes the indices of [range_dev[0], range_dev[1]) to all peers, signals, waits (at most
- * timeout_seconds: on expiry the status word of the local buffer becomes non-zero and the stream goes on).  epoch
- * counts the exchanges (1, 2, ...), identically on every rank.  Finally the n_groups indices are copied from the local
- * buffer into `index` (the exchange buffer is then free for the exchange after next). */
-#define CWQ_P2P_MAX_WORLD 8
-#define CWQ_P2P_HEADER_BYTES 512
-#define CWQ_P2P_STATUS_OFFSET 256
-CWQ_API size_t cwq_p2p_buffer_bytes(int64_t capacity_groups);
-CWQ_API int cwq_p2p_alloc(size_t bytes, void** buffer, uint8_t* h_handle64);
-CWQ_API int cwq_p2p_open(const uint8_t* h_handle64, void** peer_buffer);
-CWQ_API int cwq_p2p_close(void* peer_buffer);
-CWQ_API int cwq_p2p_free(void* buffer);
-CWQ_API int cwq_p2p_exchange_indices(const void* score_workspace, int64_t n_groups, const int64_t* range_dev,
-                             void* const* h_peer_buffers, int32_t world, int32_t rank, uint64_t epoch,
-                             int64_t capacity_groups, double timeout_seconds, uint32_t* index, void* stream);
 /* CIS:104-109 + CIS:265/347: regenerate row index[g] of every group and un-rescale:
  * sample[i] = p_scale[i] * z + p_loc[i]. */
 CWQ_API int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,

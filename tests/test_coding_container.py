@@ -40,6 +40,19 @@ def test_arithmetic_coder_round_trip_group_sizes_alphabet():
         assert coder.decode_fast(coder.encode(msg)) == [int(x) for x in msg]
 
 
+def test_arithmetic_coder_skewed_histogram_below_one_bit_per_symbol():
+    """A message with far more symbols than code bits (ADVICE r1: 2000 x symbol 3 + end symbol -> 21 bits) decodes;
+    the reference's coding.pyx has no limit on the symbols-per-bit ratio either."""
+    coder = ArithmeticCoder(np.array([1, 1, 1, 1000000]))
+    msg = [3] * 2000 + [0]
+    code = coder.encode(msg)
+    assert len(code) < 64
+    assert coder.decode_fast(''.join(code)) == msg
+    assert coder.decode(''.join(code)) == msg
+    long_msg = [3] * 300000 + [1, 2, 0]
+    assert coder.decode_fast(coder.encode(long_msg)) == long_msg
+
+
 def test_arithmetic_coder_rejects_bad_input():
     with pytest.raises(Exception, match="positive count"):
         ArithmeticCoder(np.array([3, 0, 2])).encode([1, 0])
