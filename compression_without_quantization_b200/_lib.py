@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CWQ_LIB") or os.path.join(_HERE, "libcwq.so")   # CWQ_LIB: A/B builds of the same ABI (tools/variants)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CwqError(RuntimeError):
@@ -71,8 +71,9 @@ SIGNATURES = {
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "cwq_outlier_decode": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
     "cwq_greedy_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
-    "cwq_greedy_encode": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _F32, _I64, _I64, _I32, _P, _P, _P, _SZ, _P]),
-    "cwq_greedy_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _F32, _P, _P, _P, _P]),
+    "cwq_greedy_encode": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _F32, _P, _I64, _I64, _I32, _P, _P, _P, _SZ, _P]),
+    "cwq_greedy_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _F32, _P, _P, _P, _P, _P]),
+    "cwq_greedy_shard_loc": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "cwq_unrescale": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
     "cwq_pack_workspace_bytes": (_SZ, [_I64]),
     "cwq_elias_delta_pack": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P, _P, _SZ, _P]),

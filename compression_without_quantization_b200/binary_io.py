@@ -67,8 +67,20 @@ def _pack_bits(bits):
     return np.packbits(a).tobytes()
 
 
-def write_bin_code(code, path, extras=None, extra_var_bits=None, var_length_extras=None, var_length_bits=None):
-    """BIO:69-133."""
+def _length_field(n, extra_bytes):
+    if extra_bytes == 2:
+        return bytes([n // 256, n % 256])       # BIO:97,110: raises above 65535 exactly like the reference
+    return int(n).to_bytes(extra_bytes, "big")
+
+
+def write_bin_code(code, path, extras=None, extra_var_bits=None, var_length_extras=None, var_length_bits=None, extra_bytes=2):
+    """BIO:69-133.  extra_bytes: width of the length fields in front of the arithmetic-coded blobs and the outlier lists.
+    The reference's writer hard-codes 2 (BIO:97,110) although its reader takes `extra_bytes` (BIO:136); with the default the
+    file is byte-identical to the reference's.  A 3840x2160 image can hold more than 65 535 outliers / coded bits per blob,
+    which the 16-bit fields cannot express: extra_bytes=4 is the documented extension, read back with
+    read_bin_code(..., extra_bytes=4)."""
+    if extra_bytes not in (2, 3, 4, 8):
+        raise Exception("extra_bytes must be 2 (reference format), 3, 4 or 8")
     if var_length_extras is not None:
         if var_length_bits is None or len(var_length_extras) != len(var_length_bits):
             raise Exception("Each var length extra needs to have a bitlength associated!")
@@ -78,13 +90,11 @@ def write_bin_code(code, path, extras=None, extra_var_bits=None, var_length_extr
                 f.write(int(extra % (256 ** 4)).to_bytes(4, "big"))      # BIO:84-92 keeps the low 4 bytes
         if extra_var_bits is not None:
             for bits in extra_var_bits:
-                n = len(bits)
-                f.write(bytes([n // 256, n % 256]))                     # BIO:97: 16-bit length, raises above 65535 like the reference
+                f.write(_length_field(len(bits), extra_bytes))
                 f.write(_pack_bits(bits))
         if var_length_extras is not None:
             for extra, width in zip(var_length_extras, var_length_bits):
-                n = len(extra)
-                f.write(bytes([n // 256, n % 256]))                     # BIO:110
+                f.write(_length_field(len(extra), extra_bytes))
                 f.write(bytes([width]))                                 # BIO:113
                 f.write(_pack_bits(''.join(to_bit_string(item, width) for item in extra)))
         f.write(_pack_bits(code))

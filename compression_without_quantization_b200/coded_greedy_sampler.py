@@ -19,23 +19,19 @@ __all__ = ["code_greedy_sample", "decode_greedy_sample", "code_grouped_greedy_sa
            "decode_grouped_greedy_sample", "code_grouped_greedy_sample_batch", "decode_grouped_greedy_sample_batch"]
 
 
-def _require_zero_loc(p_loc):
-    if p_loc.numel() and bool((p_loc != 0).any().item()):
-        raise CwqError("the per-group greedy entry points support proposals with loc == 0 only (every grouped call "
-                       "of the reference passes loc = 0, scale = 1: CGS:194-195, 278-281)")
-
-
 def code_greedy_sample(t_loc, t_scale, p_loc, p_scale, n_bits_per_step, n_steps, seed, rho=1.):
     """One group (CGS:29-89) -> (best_sample f32[G], bitcode bytes: n_steps indices, each
     n_bits_per_step bits LSB first)."""
     dev = E.cuda_device()
     tl, ts, pl, ps = (E.as_device_f32(x, dev) for x in (t_loc, t_scale, p_loc, p_scale))
-    _require_zero_loc(pl)
     G = tl.numel()
     if G == 0:
         return np.zeros(0, np.float32), ("0" * (int(n_bits_per_step) * int(n_steps))).encode("utf-8")
     spec = E.SegmentSpec(G, seed, 1.0, 0, float("inf"), False)
-    job = E.GreedyJob(tl, ts, pl, ps, [spec], n_steps, n_bits_per_step, rho, forced_starts=[np.array([0, G])])
+    # The shard prior is N(p_loc / n_steps, rho p_scale / sqrt(n_steps)) (CGS:42-45).  Everything is divided by p_scale only;
+    # the proposal loc enters as the per-step shard loc and the result is p_scale * best (DESIGN.md 3.8).
+    job = E.GreedyJob(tl, ts, torch.zeros_like(pl), ps, [spec], n_steps, n_bits_per_step, rho, forced_starts=[np.array([0, G])],
+                      shard_loc=E.greedy_shard_loc(pl, ps, n_steps))
     job.prepare().encode().unrescale().pack()
     n_bits = job.n_steps * job.n_bits_per_step
     bits = job.bits[:(n_bits + 7) // 8].cpu().numpy()
@@ -57,11 +53,11 @@ def decode_greedy_sample(sample_index, p_loc, p_scale, n_bits_per_step, n_steps,
     """One group (CGS:93-167) -> f32[G]."""
     dev = E.cuda_device()
     pl, ps = E.as_device_f32(p_loc, dev), E.as_device_f32(p_scale, dev)
-    _require_zero_loc(pl)
     G = pl.numel()
     if G == 0:
         return np.zeros(0, np.float32)
-    return decode_grouped_greedy_sample_batch([sample_index], [[0, G]], [_P(pl, ps)], n_bits_per_step, n_steps, seed, rho)[0]
+    return decode_grouped_greedy_sample_batch([sample_index], [[0, G]], [_P(torch.zeros_like(pl), ps)], n_bits_per_step, n_steps,
+                                              seed, rho, shard_loc=E.greedy_shard_loc(pl, ps, n_steps))[0]
 
 
 class _P:
@@ -119,8 +115,10 @@ def code_grouped_greedy_sample(sess, target, proposal, n_steps, n_bits_per_step,
     return code_grouped_greedy_sample_batch([target], [proposal], n_steps, n_bits_per_step, seed, max_group_size_bits, rho)[0]
 
 
-def decode_grouped_greedy_sample_batch(bitcodes, group_start_indices, proposals, n_bits_per_step, n_steps, seed, rho=1.):
-    """Batch of decode calls; group_start_indices[s] must already end with the number of dimensions."""
+def decode_grouped_greedy_sample_batch(bitcodes, group_start_indices, proposals, n_bits_per_step, n_steps, seed, rho=1.,
+                                       shard_loc=None):
+    """Batch of decode calls; group_start_indices[s] must already end with the number of dimensions.  shard_loc: see
+    engine.GreedyJob (device tensor over all dims of the batch, or None)."""
     dev = E.cuda_device()
     ns = len(proposals)
     seeds = list(seed) if isinstance(seed, (list, tuple)) else [seed] * ns
@@ -142,7 +140,8 @@ def decode_grouped_greedy_sample_batch(bitcodes, group_start_indices, proposals,
     pl, ps = cat(p_loc), cat(p_scale)
     sample = torch.empty(table.n, dtype=torch.float32, device=dev)
     E._lib.call("cwq_greedy_decode", E._ptr(groups.starts), E._ptr(groups.group_seed), E._ptr(groups.gid), E._ptr(indices),
-                table.n, n_steps, E.greedy_shard_scale(rho, n_steps), E._ptr(pl), E._ptr(ps), E._ptr(sample), E._stream())
+                table.n, n_steps, E.greedy_shard_scale(rho, n_steps), E._ptr(shard_loc), E._ptr(pl), E._ptr(ps), E._ptr(sample),
+                E._stream())
     host = E.to_host([sample])[0]
     return [host[table.starts[s]:table.starts[s] + sizes[s]] for s in range(ns)]
 

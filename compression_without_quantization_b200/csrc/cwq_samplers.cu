@@ -299,9 +299,12 @@ struct OutlierDeliver {
     float z[4];
     normal_quad(segs[s].seed + OUTLIER_STREAM_OFFSET, (uint32_t)local, 0u, z);
     float v = __fadd_rn(__fmul_rn(q_scale[i], z[0]), q_loc[i]);
-    sample[i] = v;
+    const uint16_t qv = quantize_u16(v);
+    // The encoder's sample carries what the decoder will reconstruct (the reference returns the unquantised draw,
+    // CIS:267, so its level-1 prior differs between encoder and decoder whenever level 2 has outliers).
+    sample[i] = dequantize_u16(qv);
     outlier_idx[pre] = local;
-    outlier_q[pre] = quantize_u16(v);
+    outlier_q[pre] = qv;
   }
 };
 __global__ void k_outlier_finish(const uint32_t* __restrict__ total, int n_seg, long long* __restrict__ off) {
@@ -312,8 +315,9 @@ __global__ void __launch_bounds__(256) k_outlier_decode(float* __restrict__ samp
                                                         const uint16_t* __restrict__ q, long long m) {
   long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  float v = dequantize_u16(q[j]);
-  if (v != 0.0f) sample[pos[j]] = v;  // CIS:361: tf.where(updates == 0, sample, updates)
+  // The listed dims are overwritten whatever the value: the reference scatters into a dense zero tensor and keeps the
+  // sample where `updates == 0` (CIS:351-361), a sentinel the explicit index list makes unnecessary.
+  sample[pos[j]] = dequantize_u16(q[j]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,6 +342,7 @@ __device__ __forceinline__ void greedy_score_quad(const float4* __restrict__ ce4
 __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* __restrict__ tparam, const long long* __restrict__ starts,
                                                                   const uint32_t* __restrict__ gseed, long long g0, int n_steps,
                                                                   uint32_t n_samples, float shard_scale,
+                                                                  const float* __restrict__ shard_loc,
                                                                   uint32_t* __restrict__ indices, float* __restrict__ best_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ ull s_warp_key[GREEDY_THREADS / 32];
@@ -360,7 +365,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
     const uint32_t sseed = 1000u * group_seed + (uint32_t)step;  // CGS:55
     for (int d = tid; d < G; d += GREEDY_THREADS) {
       float2 t = tparam[s + d];
-      ce[d].y = __fmul_rn(__fsub_rn(best[d], t.x), t.y);
+      const float b = __fadd_rn(best[d], shard_loc ? shard_loc[s + d] : 0.0f);   // the shard's loc, CGS:42,57
+      best[d] = b;
+      ce[d].y = __fmul_rn(__fsub_rn(b, t.x), t.y);
     }
     for (int j = tid; j < row_blocks(nq); j += GREEDY_THREADS) {
       BlockConst c = block_const(sseed, (uint32_t)j);
@@ -418,6 +425,7 @@ constexpr int GREEDY_CHUNK = 1024;
 __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2* __restrict__ tparam, const long long* __restrict__ starts,
                                                                     const uint32_t* __restrict__ gseed, long long g0, long long ng,
                                                                     int n_steps, uint32_t n_samples, float shard_scale,
+                                                                    const float* __restrict__ shard_loc,
                                                                     float* __restrict__ best, float2* __restrict__ ce,
                                                                     ull* __restrict__ keys, unsigned int* __restrict__ counters,
                                                                     uint32_t* __restrict__ indices) {
@@ -433,8 +441,9 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
 
   for (long long i = d_begin + (long long)blockIdx.x * blockDim.x + tid; i < d_end; i += (long long)gridDim.x * blockDim.x) {
     float2 t = tparam[i];
-    best[i] = 0.0f;
-    ce[i] = make_float2(__fmul_rn(shard_scale, t.y), __fmul_rn(__fsub_rn(0.0f, t.x), t.y));
+    const float b = __fadd_rn(0.0f, shard_loc ? shard_loc[i] : 0.0f);   // best holds "running sample + this step's shard loc"
+    best[i] = b;
+    ce[i] = make_float2(__fmul_rn(shard_scale, t.y), __fmul_rn(__fsub_rn(b, t.x), t.y));
   }
   for (long long j = (long long)blockIdx.x * blockDim.x + tid; j < ng; j += (long long)gridDim.x * blockDim.x) keys[j] = 0ull;
   grid.sync();
@@ -502,8 +511,10 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
         for (int jj = 0; jj < 4; ++jj) {
           const int d = 4 * q + jj;
           if (d < G) {
-            const float b = __fmaf_rn(shard_scale, z[jj], best[s + d]);
+            const float chosen = __fmaf_rn(shard_scale, z[jj], best[s + d]);
             const float2 t = tparam[s + d];
+            if (step + 1 == n_steps) { best[s + d] = chosen; continue; }
+            const float b = __fadd_rn(chosen, shard_loc ? shard_loc[s + d] : 0.0f);
             best[s + d] = b;
             ce[s + d].y = __fmul_rn(__fsub_rn(b, t.x), t.y);
           }
@@ -519,6 +530,7 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
 __global__ void __launch_bounds__(256) k_greedy_decode(const long long* __restrict__ starts, const uint32_t* __restrict__ gseed,
                                                        const int* __restrict__ gid, const uint32_t* __restrict__ indices,
                                                        long long n, int n_steps, float shard_scale,
+                                                       const float* __restrict__ shard_loc,
                                                        const float* __restrict__ p_loc, const float* __restrict__ p_scale,
                                                        float* __restrict__ sample) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -526,14 +538,22 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const long long* __restri
   int g = gid[i];
   uint32_t d = (uint32_t)(i - starts[g]);
   uint32_t group_seed = gseed[g];
+  const float l = shard_loc ? shard_loc[i] : 0.0f;
   float b = 0.0f;
   for (int step = 0; step < n_steps; ++step) {
     float z[4];
     normal_quad(1000u * group_seed + (uint32_t)step, indices[(long long)g * n_steps + step], d >> 2, z);
     float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
-    b = __fmaf_rn(shard_scale, zz, b);
+    b = __fmaf_rn(shard_scale, zz, __fadd_rn(b, l));
   }
   sample[i] = __fadd_rn(__fmul_rn(p_scale[i], b), p_loc[i]);
+}
+
+// loc of the proposal shard of the per-group greedy entry points, rescaled coordinates: (p_loc / n_steps) / p_scale (CGS:42)
+__global__ void __launch_bounds__(256) k_greedy_shard_loc(const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+                                                          long long n, float n_steps, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fdiv_rn(__fdiv_rn(p_loc[i], n_steps), p_scale[i]);
 }
 
 __global__ void __launch_bounds__(256) k_unrescale(const float* __restrict__ best, const float* __restrict__ p_loc,
@@ -874,7 +894,7 @@ extern "C" size_t cwq_greedy_workspace_bytes(int64_t n, int64_t n_groups, int32_
 // mode: 0 = automatic, 1 = one persistent CTA per group, 2 = lockstep units (few groups)
 extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, const uint32_t* group_seed, int64_t n_groups,
                                  int64_t g0, int64_t g1, int32_t n_steps, int32_t n_bits_per_step, float shard_scale,
-                                 int64_t max_group_size, int64_t n, int32_t mode, uint32_t* indices, float* best,
+                                 const float* shard_loc, int64_t max_group_size, int64_t n, int32_t mode, uint32_t* indices, float* best,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   CWQ_REQUIRE(n_groups > 0 && g0 >= 0 && g1 <= n_groups && g0 <= g1, "bad group range");
   CWQ_REQUIRE(n_steps > 0 && n_bits_per_step >= 0 && n_bits_per_step <= 30, "bad step parameters");
@@ -891,7 +911,8 @@ extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, con
     CWQ_REQUIRE(smem <= 200 * 1024, "group too large for shared memory (max_group_size_bits too high)");
     if (smem > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_greedy_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_greedy_encode<<<(unsigned)ng, GREEDY_THREADS, smem, st>>>(
-        (const float2*)tparam, (const long long*)starts, group_seed, g0, n_steps, 1u << n_bits_per_step, shard_scale, indices, best);
+        (const float2*)tparam, (const long long*)starts, group_seed, g0, n_steps, 1u << n_bits_per_step, shard_scale, shard_loc,
+        indices, best);
     CWQ_LAUNCH_CHECK();
     return CWQ_OK;
   }
@@ -911,7 +932,8 @@ extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, con
   const long long* a_starts = (const long long*)starts;
   long long a_g0 = g0, a_ng = ng;
   uint32_t a_ns = 1u << n_bits_per_step;
-  void* args[] = {&a_tparam, &a_starts, &group_seed, &a_g0, &a_ng, &n_steps, &a_ns, &shard_scale, &best, &ce, &keys, &counters, &indices};
+  void* args[] = {&a_tparam, &a_starts, &group_seed, &a_g0, &a_ng, &n_steps, &a_ns, &shard_scale, &shard_loc, &best, &ce, &keys,
+                  &counters, &indices};
   CWQ_CUDA(cudaLaunchCooperativeKernel((const void*)k_greedy_lockstep, dim3((unsigned)(g_sm_count * bps)), dim3(GREEDY_THREADS), args, smem, st));
   count_launches(1);
   return CWQ_OK;
@@ -919,10 +941,19 @@ extern "C" int cwq_greedy_encode(const float* tparam, const int64_t* starts, con
 
 extern "C" int cwq_greedy_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid,
                                  const uint32_t* indices, int64_t n, int32_t n_steps, float shard_scale,
-                                 const float* p_loc, const float* p_scale, float* sample, void* stream) {
+                                 const float* shard_loc, const float* p_loc, const float* p_scale, float* sample, void* stream) {
   CWQ_REQUIRE(n > 0 && n_steps > 0, "bad sizes");
   k_greedy_decode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)starts, group_seed, gid, indices,
-                                                                                n, n_steps, shard_scale, p_loc, p_scale, sample);
+                                                                                n, n_steps, shard_scale, shard_loc, p_loc, p_scale,
+                                                                                sample);
+  CWQ_LAUNCH_CHECK();
+  return CWQ_OK;
+}
+
+extern "C" int cwq_greedy_shard_loc(const float* p_loc, const float* p_scale, int64_t n, int32_t n_steps, float* shard_loc,
+                                    void* stream) {
+  CWQ_REQUIRE(n > 0 && n_steps > 0, "bad sizes");
+  k_greedy_shard_loc<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_loc, p_scale, n, (float)n_steps, shard_loc);
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }

@@ -503,13 +503,25 @@ class ISJob:
 # ----------------------------------------------------------------------------------------------
 # greedy sampler
 # ----------------------------------------------------------------------------------------------
+def greedy_shard_loc(p_loc, p_scale, n_steps):
+    """CGS:42 in rescaled coordinates: (p_loc / n_steps) / p_scale on the device."""
+    out = torch.empty_like(p_loc)
+    if p_loc.numel():
+        _lib.call("cwq_greedy_shard_loc", _ptr(p_loc), _ptr(p_scale), int(p_loc.numel()), int(n_steps), _ptr(out), _stream())
+    return out
+
+
 def greedy_shard_scale(rho, n_steps):
     """CGS:42-45 with p = N(0,1): f32(rho) / f32(sqrt(n_steps))."""
     return float(np.float32(rho) / np.float32(np.sqrt(n_steps)))
 
 
 class GreedyJob:
-    def __init__(self, q_loc, q_scale, p_loc, p_scale, specs, n_steps, n_bits_per_step, rho=1.0, forced_starts=None):
+    def __init__(self, q_loc, q_scale, p_loc, p_scale, specs, n_steps, n_bits_per_step, rho=1.0, forced_starts=None,
+                 shard_loc=None):
+        """shard_loc: per-dim loc of the proposal shard in rescaled coordinates (cwq_greedy_shard_loc), or None = 0 -- what
+        the grouped calls of the reference use (CGS:278-281); the per-group entry points pass it for p_loc != 0."""
+        self.shard_loc = shard_loc
         self.dev = q_loc.device
         self.q_loc, self.q_scale, self.p_loc, self.p_scale = q_loc, q_scale, p_loc, p_scale
         self.table = SegmentTable(specs, self.dev)
@@ -546,7 +558,7 @@ class GreedyJob:
         wsb = _lib.load().cwq_greedy_workspace_bytes(self.n, ng, self.n_steps)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
         _lib.call("cwq_greedy_encode", _ptr(self.tparam), _ptr(self.groups.starts), _ptr(self.groups.group_seed), ng, g0, g1,
-                  self.n_steps, self.n_bits_per_step, self.shard_scale, self.max_group_size, self.n, int(mode),
+                  self.n_steps, self.n_bits_per_step, self.shard_scale, _ptr(self.shard_loc), self.max_group_size, self.n, int(mode),
                   _ptr(self.indices), _ptr(self.best), _ptr(ws), wsb, _stream())
         return self
 
@@ -555,7 +567,8 @@ class GreedyJob:
         g = self.groups
         self.sample = torch.empty(self.n, dtype=torch.float32, device=self.dev)
         _lib.call("cwq_greedy_decode", _ptr(g.starts), _ptr(g.group_seed), _ptr(g.gid), _ptr(self.indices), self.n,
-                  self.n_steps, self.shard_scale, _ptr(self.p_loc), _ptr(self.p_scale), _ptr(self.sample), _stream())
+                  self.n_steps, self.shard_scale, _ptr(self.shard_loc), _ptr(self.p_loc), _ptr(self.p_scale), _ptr(self.sample),
+                  _stream())
         return self
 
     def unrescale(self):

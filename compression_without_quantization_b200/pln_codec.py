@@ -12,6 +12,12 @@ two 16-bit-length-prefixed AC blobs (group sizes of level 1, level 2, each termi
 outlier lists of level 2 (and of level 1 with importance sampling) as 24-bit indices / 16-bit values,
 then code1 + code2 zero padded to a byte.
 
+Extension for large images: the reference's 16-bit length fields (binary_io.py:97,110) overflow once a
+blob holds more than 65 535 coded bits or an outlier list more than 65 535 entries (a 3840x2160 image).  With
+`wide_length_fields="auto"` such a file is written with 32-bit length fields and bit 31 of the second extra (n_steps, always
+small) set as the marker; `decode_image_latents` recognises the marker.  Files that fit the reference format are written
+byte-identically to it; `wide_length_fields=False` keeps the reference's behaviour (an exception on overflow).
+
 Known reference behaviours kept: the decoder assumes a standard-normal level-2
 prior (pln.py:729-730); an empty first group has size 0, which is also the AC end symbol, so such a file
 cannot be decoded (the encoder warns).  The greedy level-1 path, which cannot run in the reference
@@ -27,6 +33,9 @@ from .binary_io import read_bin_code, write_bin_code
 from .coded_greedy_sampler import code_grouped_greedy_sample, decode_grouped_greedy_sample
 from .coded_importance_sampler import code_grouped_importance_sample, decode_grouped_importance_sample
 from .coding import ArithmeticCoder
+
+
+WIDE_LENGTH_FLAG = 1 << 31     # bit 31 of extras[1] (n_steps): the file has 32-bit length fields
 
 
 class _Normal:
@@ -71,7 +80,7 @@ def code_image_latents(q1, q2, p2, synthesis_2, first_level_shape, second_level_
                        second_level_n_bits_per_group=20, second_level_max_group_size_bits=4, second_level_dim_kl_bit_limit=12,
                        first_level_n_bits_per_group=20, first_level_max_group_size_bits=3, first_level_dim_kl_bit_limit=12,
                        outlier_index_bytes=3, outlier_sample_bytes=2, second_level_group_dist_counts=None,
-                       first_level_group_dist_counts=None, image_shape=None, verbose=False):
+                       first_level_group_dist_counts=None, image_shape=None, verbose=False, wide_length_fields="auto"):
     """pln.py:213-627 without the networks.  q1, q2, p2: objects with flat .loc/.scale (level-1 posterior,
     level-2 posterior and prior, UNPERMUTED); synthesis_2(latents2 with shape second_level_shape) ->
     (p1_loc, p1_scale) flat, unpermuted.  Returns ((sample2, sample1), summaries) like the reference
@@ -126,8 +135,12 @@ def code_image_latents(q1, q2, p2, synthesis_2, first_level_shape, second_level_
         print("warning: an empty group has size 0, the arithmetic coder's end symbol; the reference format cannot decode this file")
     gi1_code = coder1.encode(np.concatenate((group_differences1, [0])))
     gi2_code = coder2.encode(np.concatenate((group_differences2, [0])))
+    overflow = max([len(gi1_code), len(gi2_code)] + [len(v) for v in var_length_extras]) > 65535
+    wide = wide_length_fields is True or (wide_length_fields == "auto" and overflow)
+    if wide:
+        extras[1] |= WIDE_LENGTH_FLAG
     write_bin_code(bitcode, comp_file_path, extras=extras, extra_var_bits=[gi1_code, gi2_code],
-                   var_length_extras=var_length_extras, var_length_bits=var_length_bits)
+                   var_length_extras=var_length_extras, var_length_bits=var_length_bits, extra_bytes=4 if wide else 2)
 
     # ---- summaries (pln.py:543-577) ----
     total_kls = [_kl_nats(q1_loc, q1_scale, p1_loc_u, p1_scale_u), _kl_nats(q2_loc, q2_scale, p2_loc, p2_scale)]
@@ -164,8 +177,12 @@ def decode_image_latents(comp_file_path, synthesis_2, first_level_latent_channel
     to its synthesis_transform_1 (pln.py:815)."""
     dev = E.cuda_device()
     num_var_length_extras = 4 if use_importance_sampling else 2
+    _, extras, _, _ = read_bin_code(comp_file_path, num_extras=11)
+    wide = bool(extras[1] & WIDE_LENGTH_FLAG)
     code, extras, extra_var_bits, var_length_extras = read_bin_code(comp_file_path, num_extras=11, num_extra_var_bits=2,
-                                                                    num_var_length_extras=num_var_length_extras)
+                                                                    num_var_length_extras=num_var_length_extras,
+                                                                    extra_bytes=4 if wide else 2)
+    extras[1] &= ~WIDE_LENGTH_FLAG
     coder2 = ArithmeticCoder(_counts(second_level_group_dist_counts), precision=32)
     coder1 = ArithmeticCoder(_counts(first_level_group_dist_counts), precision=32)
     seed, n_steps, n_bits_per_step = extras[0], extras[1], extras[2]

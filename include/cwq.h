@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CWQ_ABI_VERSION 1
+#define CWQ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CWQ_API __attribute__((visibility("default")))
@@ -127,16 +127,17 @@ CWQ_API int cwq_is_shard_ranges(const int32_t* K, const int64_t* starts, int64_t
 CWQ_API int cwq_is_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid, const uint32_t* index,
                   int64_t n, const float* p_loc, const float* p_scale, float* sample, void* stream);
 
-/* CIS:148-158, 267: outliers.  sample[i] is overwritten with the (seeded) posterior draw at outlier
- * dims; outlier_idx (index inside the segment) and outlier_q (quint16 over [-30,30]) are the side
+/* CIS:148-158, 267: outliers.  sample[i] is overwritten at outlier dims with the (seeded) posterior draw AS THE DECODER
+ * WILL SEE IT, dequantise(quantise(draw)) -- the reference keeps the unquantised draw there, an encoder/decoder
+ * asymmetry; outlier_idx (index inside the segment) and outlier_q (quint16 over [-30,30]) are the side
  * information, concatenated per segment with seg_outlier_off[n_segments + 1] offsets. */
 CWQ_API size_t cwq_outlier_workspace_bytes(int64_t n);
 CWQ_API int cwq_outlier_encode(const float* q_loc, const float* q_scale, const uint8_t* mask, int64_t n,
                        const cwq_segment* segments, int32_t n_segments, float* sample, int64_t* outlier_idx,
                        uint16_t* outlier_q, int64_t* seg_outlier_off, void* workspace, size_t workspace_bytes,
                        void* stream);
-/* CIS:351-361: dequantise and scatter (dims whose dequantised value is exactly 0 keep the sample).
- * outlier_pos holds positions in the flat array. */
+/* CIS:351-361: dequantise and overwrite the listed dims (no `== 0` sentinel: the index list says which dims are
+ * outliers).  outlier_pos holds positions in the flat array. */
 CWQ_API int cwq_outlier_decode(float* sample, const int64_t* outlier_pos, const uint16_t* outlier_q, int64_t m,
                        void* stream);
 
@@ -180,16 +181,23 @@ CWQ_API int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, con
  * CGS:38-78 for groups [g0, g1): n_steps sequential steps of 2^n_bits_per_step candidates each.
  * mode 1: one persistent CTA per group, step state on chip (many groups); mode 2: all groups in lockstep,
  * (group, 1024-candidate) units claimed dynamically, two grid barriers per step (few groups, e.g. one
- * image); mode 0 picks.  Identical results.  indices[g * n_steps + j]; best[n] in rescaled coordinates. */
+ * image); mode 0 picks.  Identical results.  indices[g * n_steps + j]; best[n] in rescaled coordinates.
+ * shard_loc (may be NULL = all zero, what every grouped call of the reference passes: CGS:278-281): loc of the proposal
+ * shard per dim in rescaled coordinates, (p_loc / n_steps) / p_scale (CGS:42 `loc=p_loc / n_steps`); it is added to the
+ * running sample at the start of every step, before the candidates are scored (CGS:57).  The per-group entry points
+ * (CGS:29-36, 93-99) take any proposal loc; they rescale by p_scale only and finish with sample = p_scale * best. */
 CWQ_API size_t cwq_greedy_workspace_bytes(int64_t n, int64_t n_groups, int32_t n_steps);
 CWQ_API int cwq_greedy_encode(const float* tparam, const int64_t* starts, const uint32_t* group_seed, int64_t n_groups,
                       int64_t g0, int64_t g1, int32_t n_steps, int32_t n_bits_per_step, float shard_scale,
-                      int64_t max_group_size, int64_t n, int32_t mode, uint32_t* indices, float* best,
-                      void* workspace, size_t workspace_bytes, void* stream);
+                      const float* shard_loc, int64_t max_group_size, int64_t n, int32_t mode, uint32_t* indices,
+                      float* best, void* workspace, size_t workspace_bytes, void* stream);
 /* CGS:134-165 + CGS:292/362: replay the chosen rows and un-rescale. */
 CWQ_API int cwq_greedy_decode(const int64_t* starts, const uint32_t* group_seed, const int32_t* gid,
-                      const uint32_t* indices, int64_t n, int32_t n_steps, float shard_scale, const float* p_loc,
-                      const float* p_scale, float* sample, void* stream);
+                      const uint32_t* indices, int64_t n, int32_t n_steps, float shard_scale, const float* shard_loc,
+                      const float* p_loc, const float* p_scale, float* sample, void* stream);
+/* CGS:42: shard_loc[i] = (p_loc[i] / n_steps) / p_scale[i] (IEEE float32 divisions). */
+CWQ_API int cwq_greedy_shard_loc(const float* p_loc, const float* p_scale, int64_t n, int32_t n_steps, float* shard_loc,
+                         void* stream);
 /* sample = p_scale * best + p_loc  (CGS:292) */
 CWQ_API int cwq_unrescale(const float* best, const float* p_loc, const float* p_scale, int64_t n, float* sample,
                   void* stream);

@@ -365,7 +365,9 @@ static inline uint32_t greedy_stream_seed(uint32_t group_seed, uint32_t step) {
   return 1000u * group_seed + step; /* CGS:55  seed = 1000 * seed + i, wrapping u32 */
 }
 
-void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, int32_t G, int32_t n_steps,
+/* shard_loc (may be NULL = 0): the per-dim loc of the proposal shard in rescaled coordinates, (p_loc / n_steps) / p_scale
+ * (CGS:42 `loc=p_loc / n_steps`); every step adds it to the running sample before the candidates are scored (CGS:57). */
+void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, const float* shard_loc, int32_t G, int32_t n_steps,
                               uint32_t n_samples, float shard_scale, uint32_t group_seed, const float* inj,
                               uint32_t* indices_out, float* best_out) {
   float* isig = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1));
@@ -375,7 +377,10 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, int32_t 
   int32_t nq = (G + 3) / 4;
   for (int32_t step = 0; step < n_steps; ++step) {
     uint32_t ss = greedy_stream_seed(group_seed, (uint32_t)step);
-    for (int32_t d = 0; d < G; ++d) e[d] = (best_out[d] - t_loc[d]) * isig[d];
+    for (int32_t d = 0; d < G; ++d) {
+      best_out[d] = best_out[d] + (shard_loc ? shard_loc[d] : 0.0f);   /* the step's loc; the chosen z is added below */
+      e[d] = (best_out[d] - t_loc[d]) * isig[d];
+    }
     float best = INFINITY;
     uint32_t best_k = 0;
     for (uint32_t k = 0; k < n_samples; ++k) {
@@ -406,7 +411,7 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, int32_t 
 }
 
 /* CGS:134-165 with a counter-based stream */
-void cwqo_greedy_decode_group(int32_t G, int32_t n_steps, float shard_scale, uint32_t group_seed,
+void cwqo_greedy_decode_group(int32_t G, int32_t n_steps, float shard_scale, const float* shard_loc, uint32_t group_seed,
                               const uint32_t* indices, float* out) {
   for (int32_t d = 0; d < G; ++d) out[d] = 0.0f;
   int32_t nq = (G + 3) / 4;
@@ -415,9 +420,17 @@ void cwqo_greedy_decode_group(int32_t G, int32_t n_steps, float shard_scale, uin
     for (int32_t q = 0; q < nq; ++q) {
       float z[4];
       normal_quad(ss, indices[step], (uint32_t)q, z);
-      for (int j = 0; j < 4 && q * 4 + j < G; ++j) out[q * 4 + j] = fmaf(shard_scale, z[j], out[q * 4 + j]);
+      for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
+        int d = q * 4 + j;
+        out[d] = fmaf(shard_scale, z[j], out[d] + (shard_loc ? shard_loc[d] : 0.0f));
+      }
     }
   }
+}
+
+/* shard loc of the per-group greedy entry points in rescaled coordinates: (p_loc / n_steps) / p_scale (CGS:42) */
+void cwqo_greedy_shard_loc(const float* p_loc, const float* p_scale, int64_t n, int32_t n_steps, float* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = (p_loc[i] / (float)n_steps) / p_scale[i];
 }
 
 typedef struct { const float *t_loc, *t_scale; const int64_t* starts; int32_t n_steps; uint32_t n_samples; float shard_scale; uint32_t seed; uint32_t* indices_out; float* best_out; } gr_job_t;
@@ -425,7 +438,7 @@ static void gr_job(int64_t g, void* p) {
   gr_job_t* j = (gr_job_t*)p;
   int64_t s = j->starts[g];
   int32_t G = (int32_t)(j->starts[g + 1] - s);
-  cwqo_greedy_encode_group(j->t_loc + s, j->t_scale + s, G, j->n_steps, j->n_samples, j->shard_scale,
+  cwqo_greedy_encode_group(j->t_loc + s, j->t_scale + s, NULL, G, j->n_steps, j->n_samples, j->shard_scale,
                            j->seed + (uint32_t)g, NULL, j->indices_out + (size_t)g * j->n_steps, j->best_out + s);
 }
 /* CGS:273-284 over groups [g0, g1) on n_threads host threads */

@@ -266,7 +266,16 @@ def greedy_shard_scale(rho, n_steps):
     return float(lib().cwqo_greedy_shard_scale(ctypes.c_float(rho), ctypes.c_int32(n_steps)))
 
 
-def greedy_encode_group(t_loc, t_scale, n_steps, n_samples, shard_scale, group_seed, draws=None):
+def greedy_shard_loc(p_loc, p_scale, n_steps):
+    """CGS:42 in rescaled coordinates: (p_loc / n_steps) / p_scale, float32."""
+    p_loc, p_scale = _f32(p_loc), _f32(p_scale)
+    out = np.zeros(max(p_loc.size, 1), np.float32)
+    lib().cwqo_greedy_shard_loc(_p(p_loc, _c_f32p), _p(p_scale, _c_f32p), ctypes.c_int64(p_loc.size), ctypes.c_int32(n_steps),
+                                _p(out, _c_f32p))
+    return out[:p_loc.size]
+
+
+def greedy_encode_group(t_loc, t_scale, n_steps, n_samples, shard_scale, group_seed, draws=None, shard_loc=None):
     t_loc, t_scale = _f32(t_loc), _f32(t_scale)
     G = t_loc.size
     idx = np.zeros(n_steps, np.uint32)
@@ -275,7 +284,8 @@ def greedy_encode_group(t_loc, t_scale, n_steps, n_samples, shard_scale, group_s
     if draws is not None:
         draws = np.ascontiguousarray(draws, dtype=np.float32).reshape(n_steps, n_samples, G)
         inj = _p(draws, _c_f32p)
-    lib().cwqo_greedy_encode_group(_p(t_loc, _c_f32p), _p(t_scale, _c_f32p), ctypes.c_int32(G),
+    sl = None if shard_loc is None else _p(_f32(shard_loc), _c_f32p)
+    lib().cwqo_greedy_encode_group(_p(t_loc, _c_f32p), _p(t_scale, _c_f32p), sl, ctypes.c_int32(G),
                                    ctypes.c_int32(n_steps), ctypes.c_uint32(n_samples), ctypes.c_float(shard_scale),
                                    ctypes.c_uint32(_u32(group_seed)), inj, _p(idx, _c_u32p), _p(best, _c_f32p))
     return idx, best[:G]
@@ -399,8 +409,10 @@ def decode_importance_sample(sample_index, p_loc, p_scale, seed, use_index=False
 
 def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_group, max_group_size_bits=4,
                                    dim_kl_bit_limit=12, return_group_indices_only=False, return_indices=False,
-                                   return_indices_only=False, normal_source=None):
-    """CIS:112-274."""
+                                   return_indices_only=False, normal_source=None, outlier_mode="hardened"):
+    """CIS:112-274.  outlier_mode "reference": the returned sample carries the unquantised outlier draws (CIS:267);
+    "hardened" (what the engine does): it carries dequantise(quantise(draw)), i.e. exactly what the decoder
+    reconstructs, so that encoder and decoder agree on the level-2 sample the level-1 prior is built from."""
     _check_f32(target, "Target")
     _check_f32(proposal, "Proposal")
     q_loc, q_scale, p_loc, p_scale = map(_f32, (target.loc, target.scale, proposal.loc, proposal.scale))
@@ -439,7 +451,10 @@ def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_grou
         return tuple(indices)
     # CIS:262-267
     sample = (p_scale * sample + p_loc).astype(np.float32)
-    sample[outlier_indices] = target_samples_at_outliers
+    if outlier_mode == "reference":
+        sample[outlier_indices] = target_samples_at_outliers
+    else:
+        sample[outlier_indices] = dequantize_u16(outlier_samples)
     if return_indices:
         return sample, indices, group_start_indices, outlier_extras
     bitcode = ''.join(elias_delta_code(ix) for ix in indices).encode("utf-8")
@@ -447,8 +462,11 @@ def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_grou
 
 
 def decode_grouped_importance_sample(sess, bitcode, group_start_indices, proposal, n_bits_per_group, seed,
-                                     outlier_indices, outlier_samples, use_indices=False, normal_source=None):
-    """CIS:277-363 (use_indices follows the evident intent of CIS:88-96; the shipped branch cannot run)."""
+                                     outlier_indices, outlier_samples, use_indices=False, normal_source=None,
+                                     outlier_mode="hardened"):
+    """CIS:277-363 (use_indices follows the evident intent of CIS:88-96; the shipped branch cannot run).
+    outlier_mode "reference": dense scatter + `updates == 0` sentinel (CIS:351-361); "hardened": the listed dims are
+    overwritten, whatever their dequantised value."""
     _check_f32(proposal, "Proposal")
     p_loc, p_scale = _f32(proposal.loc), _f32(proposal.scale)
     num_dimensions = p_loc.size
@@ -470,9 +488,12 @@ def decode_grouped_importance_sample(sess, bitcode, group_start_indices, proposa
     sample = (p_scale * sample + p_loc).astype(np.float32)
     # CIS:351-361
     outlier_indices = np.asarray(outlier_indices, dtype=np.int64).reshape(-1)
-    updates = np.zeros(num_dimensions, np.float32)
-    updates[outlier_indices] = dequantize_u16(outlier_samples)
-    return np.where(updates == 0, sample, updates).astype(np.float32)
+    if outlier_mode == "reference":
+        updates = np.zeros(num_dimensions, np.float32)
+        updates[outlier_indices] = dequantize_u16(outlier_samples)
+        return np.where(updates == 0, sample, updates).astype(np.float32)
+    sample[outlier_indices] = dequantize_u16(outlier_samples)
+    return sample
 
 
 def code_greedy_sample(t_loc, t_scale, p_loc, p_scale, n_bits_per_step, n_steps, seed, rho=1., normal_source=None):
@@ -480,20 +501,27 @@ def code_greedy_sample(t_loc, t_scale, p_loc, p_scale, n_bits_per_step, n_steps,
     t_loc, t_scale, p_loc, p_scale = map(_f32, (t_loc, t_scale, p_loc, p_scale))
     G = t_loc.size
     n_samples = int(2 ** n_bits_per_step)
-    r_loc, r_scale, _ = greedy_prologue(t_loc, t_scale, p_loc, p_scale)
+    # The shard prior is N(p_loc / n_steps, rho p_scale / sqrt(n_steps)) (CGS:42-45): every step moves the running sample by
+    # p_loc / n_steps before the target scores it (CGS:57).  Spec: everything is divided by p_scale only (no loc shift), the
+    # shard loc becomes (p_loc / n_steps) / p_scale and the final sample is p_scale * best.
+    zeros = np.zeros(G, np.float32)
+    r_loc, r_scale, _ = greedy_prologue(t_loc, t_scale, zeros, p_scale)
     s = greedy_shard_scale(rho, n_steps)
+    sl = greedy_shard_loc(p_loc, p_scale, n_steps)
     draws = None
     if normal_source is not None:
         draws = np.stack([_draw(normal_source, 1000 * _u32(seed) + i, 0, n_samples, G) for i in range(n_steps)])
-    idx, best = greedy_encode_group(r_loc, r_scale, n_steps, n_samples, s, seed, draws)
-    best_sample = (p_scale * best + p_loc).astype(np.float32)
+    idx, best = greedy_encode_group(r_loc, r_scale, n_steps, n_samples, s, seed, draws, shard_loc=sl)
+    best_sample = (p_scale * best + zeros).astype(np.float32)
     return best_sample, ''.join(to_bit_string(int(i), n_bits_per_step) for i in idx)
 
 
-def _greedy_replay(G, indices, n_steps, shard_scale, group_seed, normal_source):
+def _greedy_replay(G, indices, n_steps, shard_scale, group_seed, normal_source, shard_loc=None):
     out = np.zeros(G, np.float32)
     for i in range(n_steps):
         z = np.ascontiguousarray(_draw(normal_source, 1000 * _u32(group_seed) + i, int(indices[i]), 1, G)[0])
+        if shard_loc is not None:
+            out = (out + shard_loc).astype(np.float32)
         if G > 0:
             lib().cwqo_axpy_fma(ctypes.c_float(shard_scale), _p(z, _c_f32p), _p(out, _c_f32p), ctypes.c_int64(G))
     return out
@@ -508,15 +536,16 @@ def decode_greedy_sample(sample_index, p_loc, p_scale, n_bits_per_step, n_steps,
     indices = [from_bit_string(sample_index[i:i + n_bits_per_step])
                for i in range(0, n_bits_per_step * n_steps, n_bits_per_step)]
     s = greedy_shard_scale(rho, n_steps)
+    sl = greedy_shard_loc(p_loc, p_scale, n_steps)
     if normal_source is None:
         out = np.zeros(max(G, 1), np.float32)
         idx = np.asarray(indices, dtype=np.uint32)
-        lib().cwqo_greedy_decode_group(ctypes.c_int32(G), ctypes.c_int32(n_steps), ctypes.c_float(s),
+        lib().cwqo_greedy_decode_group(ctypes.c_int32(G), ctypes.c_int32(n_steps), ctypes.c_float(s), _p(sl, _c_f32p) if G else None,
                                        ctypes.c_uint32(_u32(seed)), _p(idx, _c_u32p), _p(out, _c_f32p))
         best = out[:G]
     else:
-        best = _greedy_replay(G, indices, n_steps, s, seed, normal_source)
-    return (p_scale * best + p_loc).astype(np.float32)
+        best = _greedy_replay(G, indices, n_steps, s, seed, normal_source, sl)
+    return (p_scale * best + np.zeros(G, np.float32)).astype(np.float32)
 
 
 def code_grouped_greedy_sample(sess, target, proposal, n_steps, n_bits_per_step, seed, max_group_size_bits=12,

@@ -80,5 +80,36 @@ for name, c in containers.items():
                   "var_length_extras": c["var_length_extras"], "var_length_bits": c["var_length_bits"],
                   "read_back": [back[0], [int(x) for x in back[1]], list(back[2]), [[int(v) for v in x] for x in back[3]]]}
     print("container", name, os.path.getsize(path), "bytes")
+
+# ---- the 32-bit length-field extension: written by the ENGINE's writer, read by the REFERENCE's reader,
+# whose `extra_bytes` parameter (binary_io.py:136) already allows it.  Content is formula-generated (tests rebuild it).
+import hashlib  # noqa: E402
 import json  # noqa: E402
+import tempfile  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from compression_without_quantization_b200 import binary_io as our_bio  # noqa: E402
+
+
+def wide_case():
+    n = 70000
+    blob = ''.join('1' if (i * i) % 7 < 3 else '0' for i in range(n + 1))
+    idx = [(i * 37) % (1 << 24) for i in range(n)]
+    val = [(i * 7919) % 65536 for i in range(n)]
+    code = ''.join('1' if (i * 5) % 11 < 4 else '0' for i in range(1234))
+    return dict(code=code, extras=[42, (1 << 31) | 30, 14], extra_var_bits=[list(blob), list(blob[:77])],
+                var_length_extras=[idx, val], var_length_bits=[24, 16])
+
+
+w = wide_case()
+with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, "wide.miracle")
+    our_bio.write_bin_code(w["code"], path, extras=w["extras"], extra_var_bits=[list(x) for x in w["extra_var_bits"]],
+                           var_length_extras=w["var_length_extras"], var_length_bits=w["var_length_bits"], extra_bytes=4)
+    raw = open(path, "rb").read()
+    back = ref_bio.read_bin_code(path, num_extras=3, num_extra_var_bits=2, num_var_length_extras=2, extra_bytes=4)
+assert back[1] == w["extras"] and back[2] == [''.join(x) for x in w["extra_var_bits"]] and [list(x) for x in back[3]] == w["var_length_extras"]
+assert back[0][:len(w["code"])] == w["code"]
+meta["wide"] = {"file_sha256": hashlib.sha256(raw).hexdigest(), "file_bytes": len(raw),
+                "reference_reader_ok": True, "payload_bits": len(back[0])}
+print("container wide", len(raw), "bytes; the reference's reader (extra_bytes=4) returns what was written")
 json.dump(meta, open(os.path.join(HERE, "containers.json"), "w"))

@@ -104,5 +104,25 @@ for name, n, key, nontrivial, seed, steps, b, m in GR_CASES:
                 name + "_starts": np.asarray(starts, np.int64), name + "_decoded": np.asarray(decoded, np.float32)})
     print(name, "groups", len(starts) - 1, "bits", len(bitcode))
 
+# per-group greedy entry points with a non-zero proposal loc (CGS:29-89, 93-167: shard prior N(p_loc / n_steps, ...))
+PG_CASES = [  # name, G, key, seed, n_steps, n_bits_per_step, rho
+    ("pg0", 27, 20, 42, 5, 6, 1.0), ("pg1", 5, 21, 7, 2, 7, 0.8), ("pg2", 36, 22, 123, 4, 6, 1.0),
+]
+for name, G, key, seed, steps, b, rho in PG_CASES:
+    rng = np.random.default_rng(9000 + key)
+    f = np.float32
+    p_loc = rng.normal(size=G).astype(f)
+    p_scale = np.log1p(np.exp(rng.normal(size=G))).astype(f)
+    t_loc = (p_loc + p_scale * rng.normal(size=G) * 0.8).astype(f)
+    t_scale = (p_scale * np.exp(-np.abs(rng.normal(0, .7, G)))).astype(f)
+    with redirect_stdout(sink):
+        best, code = sess.run(list(CGS.code_greedy_sample(t_loc, t_scale, p_loc, p_scale, b, steps, seed, rho=rho)))
+        decoded = sess.run(CGS.decode_greedy_sample(code, p_loc, p_scale, b, steps, seed, rho=rho))
+    code = code.decode("utf-8") if isinstance(code, bytes) else str(code)
+    out.update({name + "_in": np.stack([t_loc, t_scale, p_loc, p_scale]), name + "_par": np.array([seed, steps, b, rho]),
+                name + "_sample": np.asarray(best, np.float32), name + "_bitcode": np.frombuffer(code.encode(), np.uint8),
+                name + "_decoded": np.asarray(decoded, np.float32)})
+    print(name, "dims", G, "bits", len(code))
+
 np.savez_compressed(os.path.join(HERE, "reference_samplers.npz"), **out)
 print("wrote", os.path.join(HERE, "reference_samplers.npz"))

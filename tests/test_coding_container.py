@@ -76,6 +76,32 @@ def test_container_is_byte_identical_and_reads_back(tmp_path, name):
     assert back[0].startswith(meta["code"])
 
 
+def test_container_wide_length_fields_extension(tmp_path):
+    """more than 65 535 outliers / coded bits per blob (a 3840x2160 image).  The file written with
+    extra_bytes=4 was read back by the REFERENCE's reader when the golden was made (containers.json 'wide'); here the
+    engine rebuilds the same bytes, reads them back, and the default 16-bit format still raises like the reference."""
+    import hashlib
+    meta = json.load(open(os.path.join(GOLD, "containers.json")))["wide"]
+    n = 70000
+    blob = ''.join('1' if (i * i) % 7 < 3 else '0' for i in range(n + 1))
+    idx = [(i * 37) % (1 << 24) for i in range(n)]
+    val = [(i * 7919) % 65536 for i in range(n)]
+    code = ''.join('1' if (i * 5) % 11 < 4 else '0' for i in range(1234))
+    extras = [42, (1 << 31) | 30, 14]
+    path = str(tmp_path / "wide.miracle")
+    bio.write_bin_code(code, path, extras=extras, extra_var_bits=[list(blob), list(blob[:77])],
+                       var_length_extras=[idx, val], var_length_bits=[24, 16], extra_bytes=4)
+    raw = open(path, "rb").read()
+    assert len(raw) == meta["file_bytes"] and hashlib.sha256(raw).hexdigest() == meta["file_sha256"] and meta["reference_reader_ok"]
+    back = bio.read_bin_code(path, num_extras=3, num_extra_var_bits=2, num_var_length_extras=2, extra_bytes=4)
+    assert back[1] == extras and back[2] == [blob, blob[:77]] and back[3] == [idx, val]
+    assert back[0][:len(code)] == code and len(back[0]) == meta["payload_bits"]
+    with pytest.raises(ValueError):        # the reference format: bytes([n // 256, ...]) overflows (binary_io.py:97,110)
+        bio.write_bin_code(code, path, extras=extras, extra_var_bits=[list(blob)])
+    with pytest.raises(ValueError):
+        bio.write_bin_code(code, path, var_length_extras=[idx], var_length_bits=[24])
+
+
 def test_container_errors_like_the_reference(tmp_path):
     with pytest.raises(Exception, match="Each var length extra needs to have a bitlength associated!"):
         bio.write_bin_code("01", str(tmp_path / "y"), var_length_extras=[[1]], var_length_bits=None)

@@ -89,15 +89,47 @@ def test_codec_file_matches_oracle_assembly_and_round_trips(tmp_path, oracle, us
     enc1[perm_1] = s1
     enc2 = np.empty(n2, np.float32)
     enc2[perm_2] = s2
-    out2 = np.zeros(n2, bool)
-    out2[perm_2[o2[3][0]]] = True
-    assert np.array_equal(d2.reshape(-1)[~out2].view(np.uint32), enc2[~out2].view(np.uint32))
-    if not out2.any():
-        out1 = np.zeros(n1, bool)
-        if use_is:
-            out1[perm_1[o1[3][0]]] = True
-        assert np.array_equal(d1.reshape(-1)[~out1].view(np.uint32), enc1[~out1].view(np.uint32))
-        assert np.all(np.abs(d1.reshape(-1)[out1] - enc1[out1]) <= 60 / 65535 + 1e-6)
+    # decode(encode) is exact, outlier dims included (the encoder returns the dequantised outlier values)
+    assert np.array_equal(d2.reshape(-1).view(np.uint32), enc2.view(np.uint32))
+    assert np.array_equal(d1.reshape(-1).view(np.uint32), enc1.view(np.uint32))
+
+
+def test_codec_round_trip_with_level2_outliers_and_wide_length_fields(tmp_path):
+    """ADVICE r1 / SURVEY 8f N2+N4: (a) level-2 outliers: the level-1 prior the encoder builds from its level-2 sample equals the
+    one the decoder builds from the 16-bit outlier values, so level 1 round-trips exactly; (b) more than 65 535 level-1
+    outliers: the container switches to 32-bit length fields and decodes; the reference format raises."""
+    import compression_without_quantization_b200 as cwq
+    from compression_without_quantization_b200 import synthetic as syn
+    shape1, shape2 = [1, 40, 60, 32], [1, 5, 6, 8]
+    n1, n2 = int(np.prod(shape1)), int(np.prod(shape2))
+
+    def synthesis(latents2):
+        import torch
+        m = latents2.float().abs().mean()      # depends on every level-2 value, outliers included
+        i = torch.arange(n1, device=latents2.device, dtype=torch.float32)
+        return 0.3 * torch.sin(i * 0.37 + m), 0.9 + 0.2 * torch.cos(i * 0.11 + 2 * m) ** 2
+    q1, q2 = [np.array(a) for a in syn.synthetic_posterior(n1, 60)], [np.array(a) for a in syn.synthetic_posterior(n2, 61)]
+    q2[0][::17], q2[1][::17] = 6.0, 0.01       # level-2 outliers (KL >> 10 bits)
+    q1[0][:70000], q1[1][:70000] = 7.0, 0.01   # 70 000 level-1 outliers: over the 16-bit count
+    counts1, counts2 = np.arange(1, 18) * 3 + 5, np.array([3, 10, 20, 30, 400])
+    p2 = syn.Normal(np.zeros(n2, np.float32), np.ones(n2, np.float32))
+    kw = dict(second_level_n_bits_per_group=12, second_level_max_group_size_bits=2, second_level_dim_kl_bit_limit=10,
+              first_level_n_bits_per_group=12, first_level_max_group_size_bits=4, first_level_dim_kl_bit_limit=10,
+              second_level_group_dist_counts=counts2, first_level_group_dist_counts=counts1)
+    path = str(tmp_path / "big.miracle")
+    args = (syn.Normal(q1[0], q1[1]), syn.Normal(q2[0], q2[1]), p2, synthesis, shape1, shape2, 42, 3, 6, 4)
+    (s2, s1), _ = cwq.code_image_latents(*args, path, use_importance_sampling=True, **kw)
+    extras = cwq.read_bin_code(path, num_extras=11)[1]
+    assert extras[1] == (1 << 31) | 3           # the wide-length marker on n_steps
+    d1, d2 = cwq.decode_image_latents(path, synthesis, shape1[3], shape2[3], use_importance_sampling=True,
+                                      second_level_group_dist_counts=counts2, first_level_group_dist_counts=counts1)
+    perm_1, perm_2 = cwq.latent_permutations(42, n1, n2)
+    enc1, enc2 = np.empty(n1, np.float32), np.empty(n2, np.float32)
+    enc1[perm_1], enc2[perm_2] = s1, s2
+    assert np.array_equal(d2.reshape(-1).view(np.uint32), enc2.view(np.uint32))
+    assert np.array_equal(d1.reshape(-1).view(np.uint32), enc1.view(np.uint32))
+    with pytest.raises(ValueError):             # the reference's 16-bit fields cannot hold this file (binary_io.py:110)
+        cwq.code_image_latents(*args, str(tmp_path / "ref.miracle"), use_importance_sampling=True, wide_length_fields=False, **kw)
 
 
 def test_empirical_dists_feed_the_codec(tmp_path):

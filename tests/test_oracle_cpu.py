@@ -136,7 +136,8 @@ def test_importance_sampler_matches_unmodified_reference_run(oracle, gold, name)
     q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
     seed, bits, m, limit = [int(x) for x in gold[name + "_par"]]
     s, code, starts, (oi, oq) = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale),
-                                                                      oracle.Normal(p_loc, p_scale), seed, bits, m, limit)
+                                                                      oracle.Normal(p_loc, p_scale), seed, bits, m, limit,
+                                                                      outlier_mode="reference")
     assert np.array_equal(starts, gold[name + "_starts"])
     assert code == gold[name + "_bitcode"].tobytes()
     assert np.array_equal(oi, gold[name + "_oidx"]) and np.array_equal(oq, gold[name + "_oq"])
@@ -146,9 +147,19 @@ def test_importance_sampler_matches_unmodified_reference_run(oracle, gold, name)
     assert np.allclose(kls, gold[name + "_group_kls"], rtol=2e-5, atol=1e-6)   # TFP KL formula vs spec kl01: same value
     if gold[name + "_decoded"].size:
         lst = [int(x) for x in starts[:-1]]
-        d = oracle.decode_grouped_importance_sample(None, code, lst, oracle.Normal(p_loc, p_scale), bits, seed, oi, oq)
+        d = oracle.decode_grouped_importance_sample(None, code, lst, oracle.Normal(p_loc, p_scale), bits, seed, oi, oq,
+                                                    outlier_mode="reference")
         assert lst[-1] == q_loc.size
         assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
+        # the hardened outlier path: the encoder's sample IS the decoder's, outliers included
+        sh = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), seed, bits,
+                                                   m, limit)[0]
+        dh = oracle.decode_grouped_importance_sample(None, code, [int(x) for x in starts[:-1]], oracle.Normal(p_loc, p_scale), bits,
+                                                     seed, oi, oq)
+        assert np.array_equal(sh, dh)
+        inl = np.ones(q_loc.size, bool)
+        inl[oi] = False
+        assert np.array_equal(sh[inl], s[inl]) and np.all(np.abs(sh[oi] - s[oi]) <= 30 / 65535 + 1e-6)
 
 
 def test_is4_covers_outliers_and_empty_first_group(gold):
@@ -169,6 +180,21 @@ def test_greedy_sampler_matches_unmodified_reference_run(oracle, gold, name):
     assert np.array_equal(d, s)
 
 
+@pytest.mark.parametrize("name", ["pg0", "pg1", "pg2"])
+def test_per_group_greedy_with_proposal_loc_matches_unmodified_reference_run(oracle, gold, name):
+    """CGS:29-89 / 93-167 with p_loc != 0: shard prior N(p_loc / n_steps, rho p_scale / sqrt(n_steps))."""
+    t_loc, t_scale, p_loc, p_scale = gold[name + "_in"]
+    seed, steps, b = [int(x) for x in gold[name + "_par"][:3]]
+    rho = float(gold[name + "_par"][3])
+    assert np.any(p_loc != 0)
+    best, code = oracle.code_greedy_sample(t_loc, t_scale, p_loc, p_scale, b, steps, seed, rho=rho)
+    assert code.encode() == gold[name + "_bitcode"].tobytes()
+    assert np.allclose(best, gold[name + "_sample"], rtol=1e-5, atol=1e-6)
+    d = oracle.decode_greedy_sample(code, p_loc, p_scale, b, steps, seed, rho=rho)
+    assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(d, best)
+
+
 def test_oracle_round_trips_and_injection_seam(oracle):
     rng = np.random.default_rng(1)
     n = 500
@@ -177,9 +203,7 @@ def test_oracle_round_trips_and_injection_seam(oracle):
     p = oracle.Normal(np.zeros(n, np.float32), np.ones(n, np.float32))
     s, code, starts, (oi, oq) = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), p, 42, 10, 3, 6)
     d = oracle.decode_grouped_importance_sample(None, code, [int(x) for x in starts[:-1]], p, 10, 42, oi, oq)
-    inl = np.ones(n, bool)
-    inl[oi] = False
-    assert np.array_equal(d[inl], s[inl]) and np.all(np.abs(d[oi] - s[oi]) <= 60 / 65535 + 1e-6)
+    assert np.array_equal(d, s)
     # an injected source that returns the default stream must change nothing; a different one must
     calls = []
 
