@@ -32,7 +32,8 @@ class ISBuffers(ctypes.Structure):
     _fields_ = [(name, ctypes.c_void_p) for name in
                 ("kl", "coef", "mask", "gid", "sample", "outlier_idx", "outlier_q", "starts", "group_seed", "total_kl", "K",
                  "index", "bit_off", "seg_group_off", "seg_outlier_off", "bits")] + [
-        ("bits_capacity_bytes", ctypes.c_size_t), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+        ("bits_capacity_bytes", ctypes.c_size_t), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("score_range_dev", ctypes.c_void_p)]
 
 
 STAGE_GROUP, STAGE_SCORE, STAGE_FINISH = 1, 2, 4
@@ -65,7 +66,9 @@ SIGNATURES = {
     "cwq_shard_ranges_workspace_bytes": (_SZ, [_I64]),
     "cwq_is_shard_ranges": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _SZ, _P]),
     "cwq_is_decode": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
-    "cwq_is_pipeline_workspace_bytes": (_SZ, [_I64, _I32]),
+    "cwq_is_pipeline_workspace_bytes": (_SZ, [_I64, _I32, _I64]),
+    "cwq_is_pipeline_shard_ranges": (ctypes.c_int, [_I64, _I32, _I64, _I32, _P, _P, _P]),
+    "cwq_set_fused_front": (ctypes.c_int, [ctypes.c_int]),
     "cwq_is_encode_pipeline": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I32, _I64, _I32, _P, _P]),
     "cwq_outlier_workspace_bytes": (_SZ, [_I64]),
     "cwq_outlier_encode": (ctypes.c_int, [_P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P, _SZ, _P]),

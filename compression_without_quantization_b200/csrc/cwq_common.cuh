@@ -144,6 +144,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_deliver(InF in, OutF out,
 
 inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass scan support: decoupled look-back over per-tile aggregates (one status word per tile).
+// Tiles must take their ids from a ticket counter (atomicAdd), so that every predecessor of a running tile is itself
+// running or done.  status[] must be zero before the kernel.  Called by ALL 32 lanes of ONE warp of the CTA;
+// returns the exclusive prefix of `aggregate` over tiles [0, tile) to every lane and publishes the inclusive one.
+// Values must stay below 2^62.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, long long tile,
+                                                                 unsigned long long aggregate) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) st_volatile_u64(&status[0], LB_INC | aggregate);
+    return 0ull;
+  }
+  if (lane == 0) st_volatile_u64(&status[tile], LB_AGG | aggregate);
+  unsigned long long excl = 0ull;
+  long long look = tile - 1;
+  for (;;) {
+    const long long idx = look - lane;
+    unsigned long long sv = LB_INC;                        // before tile 0: an inclusive prefix of 0
+    if (idx >= 0) {
+      do { sv = ld_volatile_u64(&status[idx]); } while ((sv >> 62) == 0ull);
+    }
+    const unsigned inc = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+    const int first = inc ? __ffs(inc) - 1 : 31;           // nearest predecessor holding an inclusive prefix
+    unsigned long long v = lane <= first ? (sv & LB_VAL) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if (inc) break;
+    look -= 32;
+  }
+  if (lane == 0) st_volatile_u64(&status[tile], LB_INC | (excl + aggregate));
+  return excl;
+}
+
 // tile_sums must hold scan_tiles(n) entries; total_out (device) may be null
 template <typename T, class InF, class OutF>
 cudaError_t device_exclusive_scan(InF in, OutF out, long long n, T* tile_sums, T* total_out, cudaStream_t st) {

@@ -24,19 +24,10 @@ __global__ void __launch_bounds__(256) k_is_prologue(const float* __restrict__ q
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const cwq_segment& sg = segs[find_segment(segs, n_seg, i)];
-  float limit = sg.dim_kl_bit_limit;
-  float ps = p_scale[i];
-  float tl = __fdiv_rn(__fsub_rn(q_loc[i], p_loc[i]), ps);
-  float ts = __fdiv_rn(q_scale[i], ps);
-  float kl_bits = __fdiv_rn(kl01(tl, ts), LN2_F);
-  uint8_t m = 0;
-  if (!(kl_bits <= limit)) { m |= 1; tl = 0.0f; ts = 1.0f; }
-  if (kl_bits > limit) m |= 2;
-  if (i == sg.start) m |= 4;   // first dim of a segment (outlier compaction reads its per-segment offsets here)
-  kl[i] = kl01(tl, ts);
-  float iv = __fdiv_rn(1.0f, __fmul_rn(ts, ts));
-  coef[i] = make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
-  mask[i] = m;
+  const PrologueDim r = is_prologue_dim(q_loc[i], q_scale[i], p_loc[i], p_scale[i], sg.dim_kl_bit_limit);
+  kl[i] = r.kl;
+  coef[i] = r.coef;
+  mask[i] = r.m | (i == sg.start ? 4 : 0);   // bit 2: first dim of a segment (outlier compaction reads its per-segment offsets here)
 }
 
 __global__ void __launch_bounds__(256) k_greedy_prologue(const float* __restrict__ q_loc, const float* __restrict__ q_scale,

@@ -10,6 +10,7 @@
 //   No __syncthreads, no HBM traffic beyond the 8 B/dim coefficients and 8 B/group keys.
 #include "cwq_common.cuh"
 #include "cwq_spec.cuh"
+#include "cwq_front.cuh"
 #include <atomic>
 #include <cooperative_groups.h>
 #include <cstdlib>
@@ -173,18 +174,23 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 template <bool SMALL>
 __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
-                                                         GroupRange range, const ull* __restrict__ unit_off,
-                                                         ull* __restrict__ counter, ull* __restrict__ keys) {
+                                                         GroupRange range, const ull* __restrict__ unit_off_any,
+                                                         int unit_off_is_global, ull* __restrict__ counter,
+                                                         ull* __restrict__ keys) {
   __shared__ float4 s_coef[IS_WARPS][SMALL ? 8 : 32];   // 16 or 64 (a, b) pairs per warp
   __shared__ uint4 s_quad[IS_WARPS][SMALL ? 1 : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long g0 = range.begin(), ng = range.end() - g0;
+  // unit_off[j] = units before group g0 + j: either the range's own scan (starts at 0) or a slice of the prefix over all
+  // groups that the fused front end wrote (then rebased on the first unit of the range)
+  const ull* __restrict__ unit_off = unit_off_any + (unit_off_is_global ? g0 : 0);
+  const ull u_first = unit_off[0];
   const ull n_units = unit_off[ng];
   float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
   for (;;) {
     ull u = 0;
     if (lane == 0) u = atomicAdd(counter, (ull)UNIT_BATCH);
-    u = __shfl_sync(0xffffffffu, u, 0);
+    u = __shfl_sync(0xffffffffu, u, 0) + u_first;
     if (u >= n_units) break;
     const ull u_end = u + UNIT_BATCH < n_units ? u + UNIT_BATCH : n_units;
     // group of unit u: the largest j with unit_off[j] <= u (unit_off is strictly increasing: every group has a unit).
@@ -767,34 +773,44 @@ extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
 }
 
 // groups [g0, g1) of arrays holding n_groups entries; range ends on the device where given (see GroupRange)
+// `front` (may be null): the fused front end already holds the unit prefix over all groups, initialised keys and a counter
 static int is_encode_impl(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed, int64_t n_groups,
                           GroupRange range, int64_t max_group_size, uint32_t* index, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+                          void* stream, const FrontWorkspace* front = nullptr) {
   int rc = ensure_device_props();
   if (rc != CWQ_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // scans and the index kernel cover the host-known length of the range, or the whole capacity when an end is on the device
   const long long span = (range.g0_dev || range.g1_dev) ? n_groups : range.g1 - range.g0;
-  Workspace ws(workspace, workspace_bytes);
-  ull* unit_off = ws.take<ull>((size_t)span + 1);
-  ull* keys = ws.take<ull>((size_t)n_groups);
-  ull* tile_sums = ws.take<ull>((size_t)scan_tiles(span));
-  ull* total = ws.take<ull>(1);
-  ull* counter = ws.take<ull>(1);
-  if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
-  UnitCount in{K, range};
-  UnitDeliver out{unit_off, keys, range};
-  CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, span, tile_sums, total, st)));
-  k_units_finish<<<1, 32, 0, st>>>(unit_off, range, total, counter);
-  CWQ_LAUNCH_CHECK();
+  ull *unit_off, *keys, *counter;
+  if (front) {
+    unit_off = front->unit_off;
+    keys = front->keys;
+    counter = front->scalars + FRONT_SCORE_COUNTER;
+    CWQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(ull), st));
+  } else {
+    Workspace ws(workspace, workspace_bytes);
+    unit_off = ws.take<ull>((size_t)span + 1);
+    keys = ws.take<ull>((size_t)n_groups);
+    ull* tile_sums = ws.take<ull>((size_t)scan_tiles(span));
+    ull* total = ws.take<ull>(1);
+    counter = ws.take<ull>(1);
+    if (!unit_off || !keys || !tile_sums || !total || !counter) { set_error("cwq_is_encode: workspace too small"); return CWQ_ERR_WORKSPACE; }
+    UnitCount in{K, range};
+    UnitDeliver out{unit_off, keys, range};
+    CWQ_CUDA((device_exclusive_scan<ull, UnitCount, UnitDeliver>(in, out, span, tile_sums, total, st)));
+    k_units_finish<<<1, 32, 0, st>>>(unit_off, range, total, counter);
+    CWQ_LAUNCH_CHECK();
+  }
+  const int is_global = front ? 1 : 0;
   const bool prof = g_profile && g_profile_count < PROFILE_RING;
   if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
   if (max_group_size <= 16)
     k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                              group_seed, range, unit_off, counter, keys);
+                                                                              group_seed, range, unit_off, is_global, counter, keys);
   else
     k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                                   group_seed, range, unit_off, counter, keys);
+                                                                                   group_seed, range, unit_off, is_global, counter, keys);
   CWQ_LAUNCH_CHECK();
   if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
   k_is_index<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(keys, range, index);
@@ -995,13 +1011,67 @@ extern "C" int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, con
   return CWQ_OK;
 }
 
-extern "C" size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments) {
+extern "C" size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments, int64_t max_group_size) {
   if (n <= 0 || n_segments <= 0) return 0;
   const int64_t cap = n + n_segments;
   size_t w = cwq_group_workspace_bytes(n, n_segments);
-  const size_t others[3] = {cwq_is_encode_workspace_bytes(cap), cwq_outlier_workspace_bytes(n), cwq_pack_workspace_bytes(cap)};
+  const size_t others[4] = {cwq_is_encode_workspace_bytes(cap), cwq_outlier_workspace_bytes(n), cwq_pack_workspace_bytes(cap),
+                            cwq_shard_ranges_workspace_bytes(cap)};
   for (size_t o : others) w = o > w ? o : w;
+  FrontPlan plan;
+  if (front_plan(n, max_group_size, &plan)) {
+    const size_t f = front_workspace_bytes(n, n_segments, cap, plan);
+    w = f > w ? f : w;
+  }
   return w;
+}
+
+namespace cwq {
+// bounds[r] = one past the first group whose inclusive work prefix reaches r / world of the total (same cut rule as
+// ShardCuts), from the exclusive prefix the fused front end wrote: one binary search per rank
+__global__ void k_shard_bounds_from_prefix(const ull* __restrict__ work_off, const long long* __restrict__ ng_dev, int world,
+                                           long long* __restrict__ bounds) {
+  const int r = threadIdx.x;
+  if (r > world) return;
+  const long long ng = *ng_dev;
+  if (r == 0) { bounds[0] = 0; return; }
+  if (r == world) { bounds[world] = ng; return; }
+  const ull tot = work_off[ng];
+  const ull target = tot * (ull)r;
+  long long lo = 0, hi = ng - 1;           // smallest j with work_off[j + 1] * world >= target
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (work_off[mid + 1] * (ull)world >= target) hi = mid; else lo = mid + 1;
+  }
+  bounds[r] = lo + 1;
+}
+
+static bool g_front_enabled = true;
+}  // namespace cwq
+
+extern "C" int cwq_set_fused_front(int on) {
+  const int was = g_front_enabled ? 1 : 0;
+  g_front_enabled = on != 0;
+  return was;
+}
+
+extern "C" int cwq_is_pipeline_shard_ranges(int64_t n, int32_t n_segments, int64_t max_group_size, int32_t world, int64_t* bounds,
+                                            const cwq_is_buffers* b, void* stream) {
+  CWQ_REQUIRE(b && bounds && n > 0 && n_segments > 0 && world >= 1 && world <= 1024, "bad arguments");
+  const int64_t cap = n + n_segments;
+  const int64_t* ng_dev = b->seg_group_off + n_segments;
+  FrontPlan plan;
+  if (g_front_enabled && front_plan(n, max_group_size, &plan)) {
+    FrontWorkspace fw;
+    if (!front_carve(b->workspace, b->workspace_bytes, n, n_segments, cap, plan, &fw)) {
+      set_error("cwq_is_pipeline_shard_ranges: workspace too small");
+      return CWQ_ERR_WORKSPACE;
+    }
+    k_shard_bounds_from_prefix<<<1, 1056, 0, (cudaStream_t)stream>>>(fw.work_off, (const long long*)ng_dev, world, (long long*)bounds);
+    CWQ_LAUNCH_CHECK();
+    return CWQ_OK;
+  }
+  return CWQ_ERR_ARG;
 }
 
 extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale,
@@ -1012,6 +1082,31 @@ extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, 
   const int64_t cap = n + n_segments;
   const int64_t* ng_dev = b->seg_group_off + n_segments;
   int rc = CWQ_OK;
+  FrontPlan plan;
+  if (g_front_enabled && front_plan(n, max_group_size, &plan)) {
+    // the fused front end (cwq_front.cu): 3 kernels for GROUP, the scoring kernel on the prefix they leave, 2 for FINISH
+    FrontWorkspace fw;
+    if (!front_carve(b->workspace, b->workspace_bytes, n, n_segments, cap, plan, &fw)) {
+      set_error("cwq_is_encode_pipeline: workspace too small");
+      return CWQ_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stages & CWQ_STAGE_GROUP) {
+      rc = front_group(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, plan, fw, b, st);
+      if (rc != CWQ_OK) return rc;
+    }
+    if (stages & CWQ_STAGE_SCORE) {
+      GroupRange range{0, cap, nullptr, (const long long*)ng_dev};
+      if (b->score_range_dev) range = GroupRange{0, cap, (const long long*)b->score_range_dev, (const long long*)b->score_range_dev + 1};
+      rc = is_encode_impl(b->coef, b->starts, b->K, b->group_seed, cap, range, max_group_size, b->index, nullptr, 0, stream, &fw);
+      if (rc != CWQ_OK) return rc;
+    }
+    if (stages & CWQ_STAGE_FINISH) {
+      rc = front_finish(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, cap, plan, fw, b, st);
+      if (rc != CWQ_OK) return rc;
+    }
+    return CWQ_OK;
+  }
   if (stages & CWQ_STAGE_GROUP) {
     rc = cwq_is_prologue(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, b->kl, b->coef, b->mask, stream);
     if (rc != CWQ_OK) return rc;
@@ -1022,8 +1117,12 @@ extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, 
     if (rc != CWQ_OK) return rc;
   }
   if (stages & CWQ_STAGE_SCORE) {
-    rc = cwq_is_encode(b->coef, b->starts, b->K, b->group_seed, cap, ng_dev, 0, cap, max_group_size, b->index, b->workspace,
-                       b->workspace_bytes, stream);
+    if (b->score_range_dev)
+      rc = cwq_is_encode_device_range(b->coef, b->starts, b->K, b->group_seed, cap, b->score_range_dev, max_group_size, b->index,
+                                      b->workspace, b->workspace_bytes, stream);
+    else
+      rc = cwq_is_encode(b->coef, b->starts, b->K, b->group_seed, cap, ng_dev, 0, cap, max_group_size, b->index, b->workspace,
+                         b->workspace_bytes, stream);
     if (rc != CWQ_OK) return rc;
   }
   if (stages & CWQ_STAGE_FINISH) {

@@ -272,6 +272,25 @@ __device__ __forceinline__ float kl01(float mu, float sigma) {
 
 constexpr float LN2_F = 0.6931472f;
 
+// Per-dim prologue of the importance sampler (CIS:133-163): rescale q by p, outlier test against
+// `limit` bits, KL of what stays, score coefficients (a, b).  m bit0 = dim replaced by the prior, bit1 = outlier (side info).
+struct PrologueDim { float kl; float2 coef; uint8_t m; };
+__device__ __forceinline__ PrologueDim is_prologue_dim(float ql, float qs, float pl, float ps, float limit);
+
+__device__ __forceinline__ PrologueDim is_prologue_dim(float ql, float qs, float pl, float ps, float limit) {
+  float tl = __fdiv_rn(__fsub_rn(ql, pl), ps);
+  float ts = __fdiv_rn(qs, ps);
+  const float kl_bits = __fdiv_rn(kl01(tl, ts), LN2_F);
+  PrologueDim r;
+  r.m = 0;
+  if (!(kl_bits <= limit)) { r.m |= 1; tl = 0.0f; ts = 1.0f; }
+  if (kl_bits > limit) r.m |= 2;
+  r.kl = kl01(tl, ts);
+  const float iv = __fdiv_rn(1.0f, __fmul_rn(ts, ts));
+  r.coef = make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
+  return r;
+}
+
 // candidate count of a group: K = ceil(exp(total KL)), clamped to [1, 2^31-1]
 __device__ __forceinline__ int32_t candidates_from_kl(float total) {
   float c = ceilf(detexpf(total));

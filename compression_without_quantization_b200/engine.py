@@ -359,7 +359,7 @@ class ISJob:
         n, ns = self.n, self.table.count
         cap = n + ns
         bits_cap = ((cap * 42 + 31) // 32) * 4
-        wsb = _lib.load().cwq_is_pipeline_workspace_bytes(n, ns)
+        wsb = _lib.load().cwq_is_pipeline_workspace_bytes(n, ns, max(self.table.max_size_limit, 1))
         f32, i32, i64, u8, i16 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.int16
         layout = [("kl", f32, n), ("coef", f32, 2 * n), ("mask", u8, n), ("gid", i32, n), ("sample", f32, n),
                   ("outlier_idx", i64, n), ("outlier_q", i16, n), ("starts", i64, cap + 1), ("group_seed", i32, cap),
@@ -372,6 +372,7 @@ class ISJob:
             setattr(buf, name, views[name].data_ptr())
         buf.bits_capacity_bytes = bits_cap
         buf.workspace_bytes = wsb
+        buf.score_range_dev = None
         self._buffers = buf
         for name in ("kl", "coef", "mask", "total_kl", "K", "index", "sample", "outlier_idx", "outlier_q", "seg_outlier_off",
                      "bits", "bit_off"):
@@ -437,6 +438,13 @@ class ISJob:
         """int64[world + 1] on the device: contiguous work-balanced ranges of groups, one per rank (cwq_is_shard_ranges)."""
         cap = int(self.K.numel())
         bounds = torch.empty(world + 1, dtype=torch.int64, device=self.dev)
+        if hasattr(self, "_buffers"):
+            # fused pipeline: the GROUP stage left the work prefix in the workspace -> one tiny kernel
+            rc = _lib.load().cwq_is_pipeline_shard_ranges(self.n, self.table.count, max(self.table.max_size_limit, 1), int(world),
+                                                          _ptr(bounds), ctypes.cast(ctypes.pointer(self._buffers), ctypes.c_void_p),
+                                                          _stream())
+            if rc == 0:
+                return bounds
         wsb = _lib.load().cwq_shard_ranges_workspace_bytes(cap)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
         _lib.call("cwq_is_shard_ranges", _ptr(self.K), _ptr(self.groups.starts), cap, _ptr(self.groups.n_groups_dev), int(world),
@@ -446,6 +454,13 @@ class ISJob:
     def encode_device_range(self, range_dev):
         """Score groups [range_dev[0], range_dev[1]) -- two int64 on the device -- without the host knowing the range
         (sharded runs: the rank's range is computed behind the grouping and scoring starts at once)."""
+        if hasattr(self, "_buffers"):
+            self._range_keepalive = range_dev
+            self._buffers.score_range_dev = range_dev.data_ptr()
+            try:
+                return self.launch(_lib.STAGE_SCORE)
+            finally:
+                self._buffers.score_range_dev = None
         cap = int(self.K.numel())
         wsb = _lib.load().cwq_is_encode_workspace_bytes(cap)
         if hasattr(self, "_buffers") and self._buffers.workspace_bytes >= wsb:

@@ -169,10 +169,21 @@ typedef struct cwq_is_buffers {
   int64_t* seg_outlier_off; /* [n_segments + 1]     */
   uint8_t* bits;            /* bits_capacity_bytes: a multiple of 4, >= 42 bits per group of capacity */
   size_t bits_capacity_bytes;
-  void* workspace;          /* cwq_is_pipeline_workspace_bytes(n, n_segments), shared by the stages */
+  void* workspace;          /* cwq_is_pipeline_workspace_bytes(n, n_segments, max_group_size), shared by the stages: its
+                               contents must survive from the GROUP stage to the FINISH stage of one encode */
   size_t workspace_bytes;
+  const int64_t* score_range_dev; /* NULL: the SCORE stage covers all groups; else two int64 on the device, the range
+                                     [g0, g1) of groups this rank scores (sharded runs: cwq_is_pipeline_shard_ranges) */
 } cwq_is_buffers;
-CWQ_API size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments);
+CWQ_API size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments, int64_t max_group_size);
+/* Contiguous work-balanced ranges of groups for `world` ranks (same cut rule as cwq_is_shard_ranges), computed on the
+ * device behind the GROUP stage from the work prefix that stage leaves in the workspace: bounds[world + 1] (device). */
+CWQ_API int cwq_is_pipeline_shard_ranges(int64_t n, int32_t n_segments, int64_t max_group_size, int32_t world, int64_t* bounds,
+                                 const cwq_is_buffers* h_buffers, void* stream);
+/* The pipeline runs its O(N) stages as six fused kernels (csrc/cwq_front.cu) whenever the largest size limit is <= 128;
+ * cwq_set_fused_front(0) forces the stage-by-stage kernels instead (same results; used by tests as a cross-check).
+ * Returns the previous setting. */
+CWQ_API int cwq_set_fused_front(int on);
 CWQ_API int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale,
                            int64_t n, const cwq_segment* segments, const cwq_segment* h_segments, int32_t n_segments,
                            int64_t max_group_size, int32_t stages, const cwq_is_buffers* h_buffers, void* stream);

@@ -240,6 +240,63 @@ def test_fused_pipeline_call_equals_stage_by_stage(cwq, syn):
         assert torch.equal(a.bits[:n_bytes], other.bits[:n_bytes])
 
 
+def _job_arrays(job):
+    import torch
+    ng, n = job.groups.n_groups, job.n
+    n_out, n_bits = int(job.seg_outlier_off[-1]), int(job.bit_off[ng])
+    out = {"starts": job.groups.starts[:ng + 1], "gid": job.groups.gid[:n], "group_seed": job.groups.group_seed[:ng],
+           "seg_group_off": job.groups.seg_group_off, "bits": job.bits[:(n_bits + 7) // 8],
+           "outlier_idx": job.outlier_idx[:n_out], "outlier_q": job.outlier_q[:n_out]}
+    for name in ("kl", "coef", "mask", "sample", "seg_outlier_off"):
+        out[name] = getattr(job, name)
+    for name in ("total_kl", "K", "index"):
+        out[name] = getattr(job, name)[:ng]
+    out["bit_off"] = job.bit_off[:ng + 1]
+    return {k: v.clone() for k, v in out.items()}
+
+
+def test_fused_front_end_equals_stage_kernels_sweep(cwq, syn):
+    """csrc/cwq_front.cu (tiles -> chain -> groups, decode + outliers, one-pass packing) against the stage-by-stage kernels
+    behind the same pipeline call (cwq_set_fused_front(0)): every output array bit for bit, over tile-boundary sizes, many
+    and tiny segments, every size limit up to 128, empty first groups, all-outlier and no-information inputs."""
+    import torch
+    from compression_without_quantization_b200 import _lib as L, engine as E
+    lib = L.load()
+    dev = E.cuda_device()
+    rng = np.random.default_rng(2024)
+    cases = []
+    for n in (1, 2, 31, 1023, 1024, 1025, 2047, 2049, 5000, 70001):
+        cases.append(([n], [4], 12, 10))
+    cases.append(([1024, 1024, 1024], [4, 2, 0], 10, 8))                # segment starts on tile boundaries
+    cases.append(([1] * 40 + [3000] + [1] * 5, [4] * 46, 12, 10))       # runs of one-dim segments
+    cases.append(([300, 1, 777, 2304, 5, 4096 + 17], [4, 4, 3, 2, 1, 4], 14, 11))
+    cases.append(([200000], [5], 20, 16))
+    cases.append(([150000], [6], 20, 16))
+    cases.append(([1700000], [7], 16, 12))                               # E = 129: tiles of 2048 dims
+    for _ in range(10):
+        k = int(rng.integers(1, 6))
+        cases.append(([int(rng.integers(1, 9000)) for _ in range(k)], [int(rng.integers(0, 8)) for _ in range(k)],
+                      int(rng.integers(6, 18)), int(rng.integers(4, 14))))
+    for ci, (sizes, mg, bits, limit) in enumerate(cases):
+        data = [list(syn.synthetic_posterior(nn, 700 + 13 * ci + i, i % 2 == 1)) for i, nn in enumerate(sizes)]
+        if ci % 3 == 0 and sizes[0] > 1:
+            data[0][0][0], data[0][1][0] = 0.0, 1e-4                     # dim 0 alone over the budget: empty first group
+        if ci % 4 == 1:
+            data[-1][0][:], data[-1][1][:] = data[-1][2], data[-1][3]    # q == p: zero KL everywhere in the last segment
+        if ci % 5 == 2:
+            data[0][0][:] = data[0][2] + 9.0 * data[0][3]                # every dim of segment 0 an outlier
+        t = [torch.from_numpy(np.concatenate([d[j] for d in data]).astype(np.float32)).to(dev) for j in range(4)]
+        specs = [E.SegmentSpec(sizes[i], 42 + i, bits, mg[i], limit, True) for i in range(len(sizes))]
+        fused = _job_arrays(E.ISJob(*t, specs).launch(7).sync_groups())
+        was = lib.cwq_set_fused_front(0)
+        try:
+            plain = _job_arrays(E.ISJob(*t, specs).launch(7).sync_groups())
+        finally:
+            lib.cwq_set_fused_front(was)
+        for name in plain:
+            assert torch.equal(plain[name], fused[name]), (ci, sizes, mg, bits, limit, name)
+
+
 def test_shard_ranges_on_device(cwq, syn):
     """cwq_is_shard_ranges: contiguous ranges, every rank within one group's work of an equal share, and the
     device-range scoring entry point gives the indices of the host-range one."""
