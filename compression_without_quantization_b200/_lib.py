@@ -33,7 +33,7 @@ class ISBuffers(ctypes.Structure):
                 ("kl", "coef", "mask", "gid", "sample", "outlier_idx", "outlier_q", "starts", "group_seed", "total_kl", "K",
                  "index", "bit_off", "seg_group_off", "seg_outlier_off", "bits")] + [
         ("bits_capacity_bytes", ctypes.c_size_t), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-        ("score_range_dev", ctypes.c_void_p)]
+        ("score_range_dev", ctypes.c_void_p), ("tile_segment", ctypes.c_void_p)]
 
 
 STAGE_GROUP, STAGE_SCORE, STAGE_FINISH = 1, 2, 4
@@ -53,6 +53,7 @@ SIGNATURES = {
     "cwq_launch_count": (ctypes.c_longlong, []),
     "cwq_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "cwq_profile_count": (ctypes.c_int, []),
+    "cwq_profile_kind": (ctypes.c_int, [ctypes.c_int]),
     "cwq_profile_get_ms": (ctypes.c_int, [ctypes.c_int, _P]),
     "cwq_is_prologue": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _I32, _P, _P, _P, _P]),
     "cwq_greedy_prologue": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),

@@ -36,6 +36,13 @@ void count_launches(int n);
     CWQ_CUDA(cudaGetLastError());     \
   } while (0)
 
+// optional CUDA-event timing of kernels on their launching stream (cwq_profile_*): level 1 records the scoring kernel
+// only, level 2 every kernel of the fused pipeline.  trace_begin returns a slot (or -1), trace_end closes it.
+enum TraceKind { TR_SCORE = 0, TR_FRONT_TILES = 1, TR_FRONT_CHAIN = 2, TR_FRONT_GROUPS = 3, TR_FRONT_PREFIX = 4, TR_INDEX = 5,
+                 TR_FINISH_DIMS = 6, TR_PACK = 7 };
+int trace_begin(int kind, cudaStream_t st);
+void trace_end(int slot, cudaStream_t st);
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // bump allocator over the caller's workspace
@@ -143,6 +150,88 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_deliver(InF in, OutF out,
 }
 
 inline long long scan_tiles(long long n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p);
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v);
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive prefix of per-tile aggregates across the CTAs of ONE kernel, two levels, no serial chain.
+// A decoupled look-back degenerates when every tile is resident and publishes at the same moment (tile t then walks
+// t / 32 windows back); here tiles are grouped in blocks of TP_BLOCK: every tile publishes its aggregate, the tile that
+// publishes last in its block adds the block up, and a tile's prefix is [all earlier blocks] + [earlier tiles of its own
+// block], summed in parallel by the whole CTA.  Tiles must take their ids from a ticket counter (every predecessor of a
+// running tile is then running or done); all words start at zero; values stay below 2^62.  NV values per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int TP_BLOCK = 32;
+constexpr unsigned long long TP_FLAG = 1ull << 63, TP_VAL = TP_FLAG - 1ull;
+
+template <int NV>
+struct TilePrefix {
+  unsigned long long* tile_words;    // [NV][n_tiles]
+  unsigned long long* block_words;   // [NV][n_blocks]
+  unsigned int* block_count;         // [n_blocks]
+  long long n_tiles, n_blocks;
+  __host__ __device__ static size_t words(long long n_tiles) { return (size_t)NV * (size_t)(n_tiles + (n_tiles + TP_BLOCK - 1) / TP_BLOCK) + (size_t)((n_tiles + TP_BLOCK - 1) / TP_BLOCK + 1) / 2 + 1; }
+  __host__ __device__ static TilePrefix carve(unsigned long long* base, long long n_tiles) {
+    TilePrefix p;
+    p.n_tiles = n_tiles;
+    p.n_blocks = (n_tiles + TP_BLOCK - 1) / TP_BLOCK;
+    p.tile_words = base;
+    p.block_words = base + (size_t)NV * n_tiles;
+    p.block_count = reinterpret_cast<unsigned int*>(base + (size_t)NV * (n_tiles + p.n_blocks));
+    return p;
+  }
+  // ONE thread of tile t
+  __device__ void publish(long long t, const unsigned long long (&agg)[NV]) const {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) st_volatile_u64(&tile_words[(size_t)v * n_tiles + t], TP_FLAG | agg[v]);
+    __threadfence();
+    const long long b = t / TP_BLOCK;
+    const long long first = b * TP_BLOCK;
+    const int members = (int)(first + TP_BLOCK <= n_tiles ? TP_BLOCK : n_tiles - first);
+    if (atomicAdd(&block_count[b], 1u) == (unsigned)(members - 1)) {
+      __threadfence();
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        unsigned long long s = 0;
+        for (int k = 0; k < members; ++k) s += ld_volatile_u64(&tile_words[(size_t)v * n_tiles + first + k]) & TP_VAL;
+        st_volatile_u64(&block_words[(size_t)v * n_blocks + b], TP_FLAG | s);
+      }
+    }
+  }
+  // ALL threads of tile t (after publish); sm: [NV * 33] shared words.  Returns the exclusive prefixes to every thread.
+  __device__ void exclusive(long long t, unsigned long long* sm, unsigned long long (&out)[NV]) const {
+    const long long b = t / TP_BLOCK;
+    const int in_block = (int)(t - b * TP_BLOCK);
+    unsigned long long part[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) part[v] = 0;
+    for (long long j = threadIdx.x; j < b + in_block; j += blockDim.x) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const unsigned long long* w = j < b ? &block_words[(size_t)v * n_blocks + j] : &tile_words[(size_t)v * n_tiles + b * TP_BLOCK + (j - b)];
+        unsigned long long x;
+        do { x = ld_volatile_u64(w); } while (!(x & TP_FLAG));
+        part[v] += x & TP_VAL;
+      }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part[v] += __shfl_xor_sync(0xffffffffu, part[v], o);
+      if (lane == 0) sm[v * 33 + warp] = part[v];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      unsigned long long s = 0;
+      for (int k = 0; k < nwarps; ++k) s += sm[v * 33 + k];
+      out[v] = s;
+    }
+    __syncthreads();
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Single-pass scan support: decoupled look-back over per-tile aggregates (one status word per tile).

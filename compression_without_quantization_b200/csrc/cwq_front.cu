@@ -32,22 +32,55 @@ __device__ __forceinline__ int find_segment_between(const cwq_segment* __restric
   return lo;
 }
 
-// the reference's loop body from state (size, acc) at dim idx0 until the next boundary (same as cwq_group.cu:walk), with
-// kl read from the tile's shared copy (kl_s[0] is dim tile0)
-__device__ __forceinline__ long long walk_tile(const float* __restrict__ kl_s, long long tile0, long long idx0, long long size,
-                                               float acc, const cwq_segment& sg) {
-  const long long end = sg.end;
-  const double budget = sg.n_nats_per_group;
-  const long long limit = sg.size_limit;
-  const bool strict = sg.strict != 0;
-  for (long long idx = idx0; idx < end; ++idx) {
-    const float cand = __fadd_rn(acc, kl_s[idx - tile0]);
-    const bool over = strict ? ((double)cand > budget) : ((double)cand >= budget);
-    if (size >= limit || over || idx == end - 1) return idx;
-    acc = cand;
-    size += 1;
+// Segment of dim x.  tile_segment (may be null): segment of every dim 1024 k, built by the host next to the segment table;
+// with it the lookup is one load plus a short advance instead of a binary search of dependent loads at kernel start.
+__device__ __forceinline__ int segment_of(const cwq_segment* __restrict__ segs, int n_seg, const int* __restrict__ tile_segment,
+                                          long long x) {
+  if (!tile_segment) return find_segment(segs, n_seg, x);
+  int s = tile_segment[x >> 10];
+  while (s + 1 < n_seg && segs[s + 1].start <= x) ++s;
+  return s;
+}
+
+// The budget test of the reference compares the float32 running sum, promoted to double, with the float64 budget
+// n_bits * ln 2 - 1 (CIS:181,188 / CGS:226,233).  (double)x > b  <=>  x >= [smallest float32 above b], and
+// (double)x >= b  <=>  x >= [smallest float32 at or above b]: one float32 compare per step, same decisions (NaN: never over).
+__device__ __forceinline__ float kl_threshold(double budget, bool strict) {
+  float t = __double2float_ru(budget);
+  if (strict && (double)t == budget) {
+    uint32_t u = __float_as_uint(t);
+    if ((u << 1) == 0u) u = 1u;                       // +-0 -> smallest positive subnormal
+    else u = (u >> 31) ? u - 1u : u + 1u;
+    t = __uint_as_float(u);
   }
-  return end;
+  return t;
+}
+
+struct SegLocal {      // a segment seen from a tile: positions relative to the tile's first dim
+  int start, end;      // clipped to int range (n < 2^31)
+  int limit;
+  float thr;
+};
+__device__ __forceinline__ SegLocal seg_local(const cwq_segment& sg, long long tile0) {
+  SegLocal r;
+  const long long a = sg.start - tile0, b = sg.end - tile0;
+  r.start = a < -2147483000LL ? -2147483000 : (int)a;
+  r.end = b > 2147483000LL ? 2147483000 : (int)b;
+  r.limit = sg.size_limit > 2147483000LL ? 2147483000 : (int)sg.size_limit;
+  r.thr = kl_threshold(sg.n_nats_per_group, sg.strict != 0);
+  return r;
+}
+
+// the reference's loop body from state (size, acc) at local dim j0 until the next boundary (cwq_group.cu:walk restated on
+// the tile's shared copy of kl, 32-bit indices, float32 threshold)
+__device__ __forceinline__ int walk_tile(const float* __restrict__ kl_s, int j0, int size, float acc, const SegLocal& sg) {
+  for (int j = j0; j < sg.end; ++j) {
+    const float cand = __fadd_rn(acc, kl_s[j]);
+    if (size >= sg.limit || cand >= sg.thr || j == sg.end - 1) return j;
+    acc = cand;
+    ++size;
+  }
+  return sg.end;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -58,69 +91,87 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_tiles(
     const float* __restrict__ p_scale, long long n, const cwq_segment* __restrict__ segs, int n_seg, int T, int E,
     float* __restrict__ kl, float2* __restrict__ coef, uint8_t* __restrict__ mask, uint8_t* __restrict__ hop,
     int* __restrict__ seg_first, uint8_t* __restrict__ maps, uint16_t* __restrict__ counts, uint32_t* __restrict__ rows,
-    uint32_t* __restrict__ tile_out) {
+    uint32_t* __restrict__ tile_out, const int* __restrict__ tile_segment) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = T >> 5;
   float* kl_s = reinterpret_cast<float*>(smem_raw);                                   // [T + E]
   uint32_t* rows_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)(T + E) * 4);     // [E * W]
   uint8_t* hop_s = smem_raw + (size_t)(T + E) * 4 + (size_t)E * W * 4;                // [T]
-  __shared__ int s_seg[2];
   __shared__ uint32_t s_out;
   const int tid = threadIdx.x;
   const long long t = blockIdx.x;
   const long long tile0 = t * T;
-  const long long tile_end = tile0 + T < n ? tile0 + T : n;
-  const long long halo_end = tile0 + T + E < n ? tile0 + T + E : n;
-  if (tid == 0) {
-    s_seg[0] = find_segment(segs, n_seg, tile0);
-    s_seg[1] = find_segment(segs, n_seg, halo_end - 1);
-    s_out = 0;
-  }
+  const int lim = (int)(tile0 + T < n ? T : n - tile0);                 // dims of the tile
+  const int hlim = (int)(tile0 + T + E < n ? T + E : n - tile0);        // ... and of the halo behind it
+  // every thread looks the two segments up itself (same addresses: broadcast loads), so nothing waits on a barrier for it
+  const int slo = segment_of(segs, n_seg, tile_segment, tile0), shi = segment_of(segs, n_seg, tile_segment, tile0 + hlim - 1);
+  if (tid == 0) s_out = 0;
   for (int j = tid; j < E * W; j += FRONT_THREADS) rows_s[j] = 0u;
-  __syncthreads();
-  const int slo = s_seg[0], shi = s_seg[1];
+  const bool one_seg = slo == shi;                // the common case: tile and halo inside one segment
+  const cwq_segment seg0 = segs[slo];
+  const SegLocal sl0 = seg_local(seg0, tile0);
 
   // ---- prologue of the tile's dims and of the halo the boundary walks look at ----
   uint32_t my_out = 0;
-  for (long long li = tid; li < halo_end - tile0; li += FRONT_THREADS) {
+  for (int li = tid; li < hlim; li += FRONT_THREADS) {
     const long long i = tile0 + li;
-    const int s = find_segment_between(segs, slo, shi, i);
-    const PrologueDim r = is_prologue_dim(q_loc[i], q_scale[i], p_loc[i], p_scale[i], segs[s].dim_kl_bit_limit);
+    float limit = seg0.dim_kl_bit_limit;
+    bool first = li == sl0.start;
+    if (!one_seg) {
+      const int s = find_segment_between(segs, slo, shi, i);
+      limit = segs[s].dim_kl_bit_limit;
+      first = i == segs[s].start;
+    }
+    const PrologueDim r = is_prologue_dim(q_loc[i], q_scale[i], p_loc[i], p_scale[i], limit);
     kl_s[li] = r.kl;
     if (li < T) {
       kl[i] = r.kl;
       coef[i] = r.coef;
-      mask[i] = r.m | (i == segs[s].start ? 4 : 0);
+      mask[i] = r.m | (first ? 4 : 0);
       my_out += (r.m >> 1) & 1u;
     }
   }
   __syncthreads();
 
   // ---- next boundary from every dim of the tile ----
-  for (long long li = tid; li < tile_end - tile0; li += FRONT_THREADS) {
-    const long long i = tile0 + li;
-    const int s = find_segment_between(segs, slo, shi, i);
-    const cwq_segment sg = segs[s];
-    long long r;
-    if (i == sg.end - 1) r = (s + 1 < n_seg) ? walk_tile(kl_s, tile0, segs[s + 1].start, 0, 0.0f, segs[s + 1]) : n;
-    else r = walk_tile(kl_s, tile0, i + 1, 1, kl_s[li], sg);
-    const uint8_t h = (uint8_t)(r - i);
+  for (int li = tid; li < lim; li += FRONT_THREADS) {
+    int r;
+    if (one_seg) {
+      if (li == sl0.end - 1) r = (int)(n - tile0);        // last dim of the last segment (one_seg: nothing follows in the halo)
+      else r = walk_tile(kl_s, li + 1, 1, kl_s[li], sl0);
+      if (li == sl0.start) seg_first[slo] = (int)(tile0 + walk_tile(kl_s, li, 0, 0.0f, sl0));
+    } else {
+      const long long i = tile0 + li;
+      const int s = find_segment_between(segs, slo, shi, i);
+      const cwq_segment sg = segs[s];
+      const SegLocal sl = seg_local(sg, tile0);
+      if (li == sl.end - 1) {
+        if (s + 1 < n_seg) {
+          const SegLocal nx = seg_local(segs[s + 1], tile0);
+          r = walk_tile(kl_s, nx.start, 0, 0.0f, nx);
+        } else {
+          r = (int)(n - tile0);
+        }
+      } else {
+        r = walk_tile(kl_s, li + 1, 1, kl_s[li], sl);
+      }
+      if (li == sl.start) seg_first[s] = (int)(tile0 + walk_tile(kl_s, li, 0, 0.0f, sl));   // end of the segment's first group
+    }
+    const uint8_t h = (uint8_t)(r - li);
     hop_s[li] = h;
-    hop[i] = h;
-    if (i == sg.start) seg_first[s] = (int)walk_tile(kl_s, tile0, i, 0, 0.0f, sg);   // end of the segment's first group
+    hop[tile0 + li] = h;
   }
   __syncthreads();
 
   // ---- the chain through the tile from each possible entry offset ----
   if (tid < E) {
-    const long long lim = tile_end - tile0;
-    long long v = tid;
+    int v = tid;
     int cnt = 0;
     uint32_t* row = rows_s + (size_t)tid * W;
     int cur_w = -1;
     uint32_t acc = 0u;
     while (v < lim) {
-      const int w = (int)(v >> 5);
+      const int w = v >> 5;
       if (w != cur_w) {
         if (cur_w >= 0) row[cur_w] = acc;
         cur_w = w;
@@ -172,7 +223,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_front_chain(
   const int W = T >> 5;
 
   for (long long j = tid; j < n_tiles * E; j += CHAIN_THREADS) maps_s[j] = maps[j];
-  for (long long j = tid; j < 2 * n_tiles; j += CHAIN_THREADS) status[j] = 0ull;   // look-back words of k_front_groups
+  for (long long j = tid; j < (long long)TilePrefix<2>::words(n_tiles); j += CHAIN_THREADS) status[j] = 0ull;   // tile-prefix words of k_front_groups
   if (tid < 8) scalars[tid] = 0ull;                                                  // tickets / counters of later kernels
   __syncthreads();
   // level 1: entry -> exit of each block of CHAIN_BLOCK tiles
@@ -263,6 +314,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_front_chain(
 // kernel 3: groups of each tile
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ ull units_of(int K) { return (ull)((K + FRONT_UNIT_CAND - 1) / FRONT_UNIT_CAND); }
+__device__ __forceinline__ ull work_of(int K, int dims) {
+  const int blocks = row_blocks((dims + 3) >> 2);
+  return (ull)K * (ull)(blocks > 0 ? blocks : 1);
+}
 
 __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
     long long n, const cwq_segment* __restrict__ segs, int n_seg, int T, int E, long long n_tiles,
@@ -270,38 +325,32 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
     const uint32_t* __restrict__ rows, const uint8_t* __restrict__ entry, const uint32_t* __restrict__ base,
     const long long* __restrict__ seg_group_off, long long* __restrict__ starts, int* __restrict__ gid,
     uint32_t* __restrict__ group_seed, float* __restrict__ total_kl, int* __restrict__ K, ull* __restrict__ keys,
-    ull* __restrict__ unit_off, ull* __restrict__ work_off, ull* __restrict__ status, ull* __restrict__ scalars) {
+    ull* __restrict__ unit_off, ull* __restrict__ work_off, ull* __restrict__ prefix_words, const int* __restrict__ tile_segment) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = T >> 5;
-  uint32_t* node_w = reinterpret_cast<uint32_t*>(smem_raw);     // [W] chain nodes of the tile
-  uint32_t* seg_w = node_w + W;                                 // [W] segment starts of the tile
-  uint32_t* node_pre = seg_w + W;                               // [W] nodes before each word
-  uint32_t* seg_pre = node_pre + W;                             // [W]
-  __shared__ ull sm_scan[33];
-  __shared__ long long s_tile;
-  __shared__ int s_seg[2];
-  __shared__ ull s_excl[2];
+  float* kl_s = reinterpret_cast<float*>(smem_raw);                        // [T + E] the tile's kl and the halo behind it
+  uint32_t* node_w = reinterpret_cast<uint32_t*>(kl_s + T + E);            // [W] chain nodes of the tile
+  uint32_t* seg_w = node_w + W;                                            // [W] segment starts of the tile
+  uint32_t* node_pre = seg_w + W;                                          // [W] nodes before each word
+  uint32_t* seg_pre = node_pre + W;                                        // [W]
+  uint8_t* hop_s = reinterpret_cast<uint8_t*>(seg_pre + W);                // [T]
+  __shared__ ull sm_scan[2 * 33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = (long long)atomicAdd(&scalars[FRONT_TICKET_GROUPS], 1ull);   // ticket order: look-back needs it
-  __syncthreads();
-  const long long t = s_tile;
+  const long long t = blockIdx.x;
   const long long tile0 = t * T;
-  const long long tile_end = tile0 + T < n ? tile0 + T : n;
+  const int lim = (int)(tile0 + T < n ? T : n - tile0);
+  const int hlim = (int)(tile0 + T + E < n ? T + E : n - tile0);
   const uint32_t B = base[t];
-  for (int w = tid; w < W; w += FRONT_THREADS) {
-    node_w[w] = rows[((size_t)t * E + entry[t]) * W + w];
-    seg_w[w] = 0u;
-  }
-  if (tid == 0) {
-    s_seg[0] = find_segment(segs, n_seg, tile0);
-    s_seg[1] = find_segment(segs, n_seg, tile_end - 1);
-  }
+  const uint32_t* __restrict__ row = rows + ((size_t)t * E + entry[t]) * W;
+  for (int w = tid; w < W; w += FRONT_THREADS) { node_w[w] = row[w]; seg_w[w] = 0u; }
+  for (int j = tid; j < hlim; j += FRONT_THREADS) kl_s[j] = kl[tile0 + j];
+  for (int j = tid; j < lim; j += FRONT_THREADS) hop_s[j] = hop[tile0 + j];
+  const int slo = segment_of(segs, n_seg, tile_segment, tile0), shi = segment_of(segs, n_seg, tile_segment, tile0 + lim - 1);
   __syncthreads();
-  const int slo = s_seg[0], shi = s_seg[1];
   if (tid == 0) {
     for (int s = slo; s <= shi; ++s) {
       const long long p = segs[s].start;
-      if (p >= tile0 && p < tile_end) seg_w[(p - tile0) >> 5] |= 1u << ((p - tile0) & 31);
+      if (p >= tile0 && p < tile0 + lim) seg_w[(p - tile0) >> 5] |= 1u << ((p - tile0) & 31);
     }
   }
   __syncthreads();
@@ -323,141 +372,92 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
   }
   __syncthreads();
 
-  // each thread owns D consecutive dims: thread order == group order
+  // each thread owns D consecutive dims: thread order == group order, and a thread's groups have consecutive indices
   const int D = T / FRONT_THREADS;
-  const long long li0 = (long long)tid * D;
+  const int li0 = tid * D;
   ull my_units = 0, my_work = 0;
-  for (int r = 0; r < D; ++r) {
-    const long long li = li0 + r, i = tile0 + li;
-    if (i >= tile_end) break;
-    const int w = (int)(li >> 5), b = (int)(li & 31);
-    const uint32_t le = b == 31 ? 0xffffffffu : ((2u << b) - 1u);
-    const uint32_t nodes_le = node_pre[w] + __popc(node_w[w] & le), segs_le = seg_pre[w] + __popc(seg_w[w] & le);
-    const uint32_t is_node = (node_w[w] >> b) & 1u, is_seg = (seg_w[w] >> b) & 1u;
-    gid[i] = (int)(B + nodes_le + segs_le) - 1;
-    if (!(is_node | is_seg)) continue;
-    const int s = find_segment_between(segs, slo, shi, i);
-    const uint32_t seed0 = segs[s].seed;
-    const long long seg_end = segs[s].end;
-    const long long goff = seg_group_off[s];
-    for (int which = 0; which < 2; ++which) {      // 0: the segment's forced first group, 1: the chain node's group
-      if (which == 0 ? !is_seg : !is_node) continue;
-      const long long g = which == 0 ? (long long)(B + (nodes_le - is_node) + (segs_le - 1)) : (long long)(B + nodes_le - 1 + segs_le);
-      // a node's group ends at the next node -- or at the end of its segment (the last dim of a segment hops into the next one)
-      const long long end = which == 0 ? (long long)seg_first[s] : (i + hop[i] < seg_end ? i + hop[i] : seg_end);
-      float acc = 0.0f;
-      for (long long k = i; k < end; ++k) acc = __fadd_rn(acc, kl[k]);
-      const int Kg = candidates_from_kl(acc);
-      starts[g] = i;
-      total_kl[g] = acc;
-      K[g] = Kg;
-      group_seed[g] = seed0 + (uint32_t)(g - goff);
-      keys[g] = KEY_INIT;
-      my_units += units_of(Kg);
-      const int nq = (int)((end - i + 3) >> 2);
-      const int blocks = row_blocks(nq);
-      my_work += (ull)Kg * (ull)(blocks > 0 ? blocks : 1);
+  long long g_first = -1;
+  int g_count = 0;
+  if (li0 < lim) {
+    const int w0 = li0 >> 5, b0 = li0 & 31;
+    const uint32_t below = (1u << b0) - 1u;
+    uint32_t nodes = node_pre[w0] + __popc(node_w[w0] & below);     // chain nodes / segment starts strictly before li0
+    uint32_t sstarts = seg_pre[w0] + __popc(seg_w[w0] & below);
+    const bool one_seg = slo == shi;
+    for (int r = 0; r < D && li0 + r < lim; ++r) {
+      const int li = li0 + r;
+      const uint32_t is_node = (node_w[li >> 5] >> (li & 31)) & 1u, is_seg = (seg_w[li >> 5] >> (li & 31)) & 1u;
+      if (is_node | is_seg) {
+        const int s = one_seg ? slo : find_segment_between(segs, slo, shi, tile0 + li);
+        const cwq_segment& sg = segs[s];
+        const uint32_t seed0 = sg.seed;
+        const long long goff = seg_group_off[s];
+        const long long seg_end_l = sg.end - tile0;
+        for (int which = 0; which < 2; ++which) {      // 0: the segment's forced first group, 1: the chain node's group
+          if (which == 0 ? !is_seg : !is_node) continue;
+          const long long g = (long long)B + nodes + sstarts + (which == 1 ? is_seg : 0u);
+          // a node's group ends at the next node -- or at the end of its segment (the last dim of a segment hops into the next one)
+          long long end_l = which == 0 ? (long long)seg_first[s] - tile0 : (long long)li + hop_s[li];
+          if (end_l > seg_end_l) end_l = seg_end_l;
+          float acc = 0.0f;
+          for (int k = li; k < (int)end_l; ++k) acc = __fadd_rn(acc, kl_s[k]);
+          const int Kg = candidates_from_kl(acc);
+          starts[g] = tile0 + li;
+          total_kl[g] = acc;
+          K[g] = Kg;
+          group_seed[g] = seed0 + (uint32_t)(g - goff);
+          keys[g] = KEY_INIT;
+          unit_off[g] = my_units;           // relative to this thread's first group; completed below
+          work_off[g] = my_work;
+          my_units += units_of(Kg);
+          my_work += work_of(Kg, (int)end_l - li);
+          if (g_first < 0) g_first = g;
+          ++g_count;
+        }
+      }
+      nodes += is_node;
+      sstarts += is_seg;
+      gid[tile0 + li] = (int)(B + nodes + sstarts) - 1;
     }
   }
-  ull tot_units, tot_work;
-  ull upre = block_exclusive_scan<ull>(my_units, sm_scan, tot_units);
-  ull wpre = block_exclusive_scan<ull>(my_work, sm_scan, tot_work);
-  if (warp == 0) {
-    const ull eu = lookback_exclusive(status, t, tot_units);
-    const ull ew = lookback_exclusive(status + n_tiles, t, tot_work);
-    if (lane == 0) { s_excl[0] = eu; s_excl[1] = ew; }
+  ull tot_u, tot_w;
+  ull upre = block_exclusive_scan<ull>(my_units, sm_scan, tot_u);
+  ull wpre = block_exclusive_scan<ull>(my_work, sm_scan, tot_w);
+  // prefixes relative to the tile; the tile's totals are published for k_front_prefix, which completes them
+  for (int k = 0; k < g_count; ++k) {
+    unit_off[g_first + k] += upre;
+    work_off[g_first + k] += wpre;
   }
-  __syncthreads();
-  upre += s_excl[0];
-  wpre += s_excl[1];
-  for (int r = 0; r < D; ++r) {
-    const long long li = li0 + r, i = tile0 + li;
-    if (i >= tile_end) break;
-    const int w = (int)(li >> 5), b = (int)(li & 31);
-    const uint32_t is_node = (node_w[w] >> b) & 1u, is_seg = (seg_w[w] >> b) & 1u;
-    if (!(is_node | is_seg)) continue;
-    const uint32_t le = b == 31 ? 0xffffffffu : ((2u << b) - 1u);
-    const uint32_t nodes_le = node_pre[w] + __popc(node_w[w] & le), segs_le = seg_pre[w] + __popc(seg_w[w] & le);
-    const int s = find_segment_between(segs, slo, shi, i);
-    const long long seg_end = segs[s].end;
-    for (int which = 0; which < 2; ++which) {
-      if (which == 0 ? !is_seg : !is_node) continue;
-      const long long g = which == 0 ? (long long)(B + (nodes_le - is_node) + (segs_le - 1)) : (long long)(B + nodes_le - 1 + segs_le);
-      // a node's group ends at the next node -- or at the end of its segment (the last dim of a segment hops into the next one)
-      const long long end = which == 0 ? (long long)seg_first[s] : (i + hop[i] < seg_end ? i + hop[i] : seg_end);
-      const int Kg = K[g];
-      unit_off[g] = upre;
-      work_off[g] = wpre;
-      upre += units_of(Kg);
-      const int nq = (int)((end - i + 3) >> 2);
-      const int blocks = row_blocks(nq);
-      wpre += (ull)Kg * (ull)(blocks > 0 ? blocks : 1);
-    }
-  }
-  if (t == n_tiles - 1 && tid == FRONT_THREADS - 1) {   // the thread holding the last groups closes both prefixes
-    const long long ng = seg_group_off[n_seg];
-    unit_off[ng] = upre;
-    work_off[ng] = wpre;
+  if (tid == 0) {
+    const TilePrefix<2> tp = TilePrefix<2>::carve(prefix_words, n_tiles);
+    const ull agg[2] = {tot_u, tot_w};
+    tp.publish(t, agg);
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// after the scoring kernel: regenerate the chosen rows, un-rescale, outliers (CIS:104-109, 148-158, 262-267)
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRONT_THREADS) k_finish_dims(
-    long long n, const cwq_segment* __restrict__ segs, int n_seg, int T, const float* __restrict__ q_loc,
-    const float* __restrict__ q_scale, const float* __restrict__ p_loc, const float* __restrict__ p_scale,
-    const uint8_t* __restrict__ mask, const long long* __restrict__ starts, const uint32_t* __restrict__ gseed,
-    const int* __restrict__ gid, const uint32_t* __restrict__ index, const uint32_t* __restrict__ tile_out_off,
-    float* __restrict__ sample, long long* __restrict__ outlier_idx, uint16_t* __restrict__ outlier_q,
-    long long* __restrict__ seg_outlier_off, ull* __restrict__ pack_status, long long pack_tiles, ull* __restrict__ scalars) {
-  __shared__ uint32_t sm_scan[33];
-  const int tid = threadIdx.x;
+// kernel 3b: add to every group the units / work of the tiles before its own (all tiles have published: nothing waits)
+constexpr int PREFIX_THREADS = 64;
+__global__ void __launch_bounds__(PREFIX_THREADS) k_front_prefix(long long n_tiles, const uint32_t* __restrict__ base,
+                                                                 const long long* __restrict__ ng_dev, ull* __restrict__ unit_off,
+                                                                 ull* __restrict__ work_off, ull* __restrict__ prefix_words) {
+  __shared__ ull sm[2 * 33];
   const long long t = blockIdx.x;
-  // the packing kernel that follows on the stream starts from clean look-back words and a clean ticket
-  for (long long j = t * FRONT_THREADS + tid; j < pack_tiles; j += (long long)gridDim.x * FRONT_THREADS) pack_status[j] = 0ull;
-  if (t == 0 && tid == 0) scalars[FRONT_TICKET_PACK] = 0ull;
-  const long long tile0 = t * T;
-  const long long tile_end = tile0 + T < n ? tile0 + T : n;
-  const int D = T / FRONT_THREADS;
-  const long long i0 = tile0 + (long long)tid * D;
-  uint32_t my_out = 0;
-  for (int r = 0; r < D; ++r) {
-    const long long i = i0 + r;
-    if (i >= tile_end) break;
-    my_out += (mask[i] >> 1) & 1u;
+  const TilePrefix<2> tp = TilePrefix<2>::carve(prefix_words, n_tiles);
+  ull excl[2];
+  tp.exclusive(t, sm, excl);
+  const long long ng = *ng_dev;
+  const long long g0 = base[t], g1 = t + 1 < n_tiles ? (long long)base[t + 1] : ng;
+  for (long long g = g0 + threadIdx.x; g < g1; g += PREFIX_THREADS) {
+    unit_off[g] += excl[0];
+    work_off[g] += excl[1];
   }
-  uint32_t tot;
-  uint32_t pre = block_exclusive_scan<uint32_t>(my_out, sm_scan, tot) + tile_out_off[t];
-  for (int r = 0; r < D; ++r) {
-    const long long i = i0 + r;
-    if (i >= tile_end) break;
-    const uint8_t m = mask[i];
-    int s = -1;
-    if (m & 6) s = find_segment(segs, n_seg, i);
-    if (m & 4) seg_outlier_off[s] = (long long)pre;       // outliers before this segment
-    if (m & 2) {
-      const long long local = i - segs[s].start;
-      float z[4];
-      normal_quad(segs[s].seed + OUTLIER_STREAM_OFFSET, (uint32_t)local, 0u, z);
-      const float v = __fadd_rn(__fmul_rn(q_scale[i], z[0]), q_loc[i]);
-      const uint16_t qv = quantize_u16(v);
-      sample[i] = dequantize_u16(qv);
-      outlier_idx[pre] = local;
-      outlier_q[pre] = qv;
-      ++pre;
-    } else {
-      const int g = gid[i];
-      const uint32_t d = (uint32_t)(i - starts[g]);
-      float z[4];
-      normal_quad(gseed[g], index[g], d >> 2, z);
-      const float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
-      sample[i] = __fadd_rn(__fmul_rn(p_scale[i], zz), p_loc[i]);
-    }
+  if (t == n_tiles - 1 && threadIdx.x == 0) {
+    unit_off[ng] = excl[0] + (ld_volatile_u64(&tp.tile_words[t]) & TP_VAL);
+    work_off[ng] = excl[1] + (ld_volatile_u64(&tp.tile_words[n_tiles + t]) & TP_VAL);
   }
 }
 
-// Elias-delta packing of index + 1 (BIO:7-20), one pass: per-tile bit counts, look-back, atomicOr of byte-swapped words
+// Elias-delta code of index + 1 (BIO:7-20)
 __device__ __forceinline__ void elias_delta_bits(uint32_t x, ull& pattern, int& len) {
   const int nb = 31 - __clz((int)x);
   const int l = 31 - __clz(nb + 1);
@@ -480,51 +480,147 @@ __device__ __forceinline__ void put_bits_bytes(uint32_t* words, ull pos, ull pat
   }
 }
 
-constexpr int PACK_ITEMS = 8;
-constexpr int PACK_TILE = FRONT_THREADS * PACK_ITEMS;
-
-__global__ void __launch_bounds__(FRONT_THREADS) k_pack_elias(const uint32_t* __restrict__ index, long long n_groups_cap,
-                                                              const long long* __restrict__ ng_dev, uint32_t* __restrict__ words,
-                                                              long long* __restrict__ bit_off, ull* __restrict__ status,
-                                                              ull* __restrict__ scalars) {
-  __shared__ ull sm_scan[33];
-  __shared__ long long s_tile;
-  __shared__ ull s_excl;
+// ------------------------------------------------------------------------------------------------------------------
+// after the scoring kernel: regenerate the chosen rows, un-rescale, outliers (CIS:104-109, 148-158, 262-267)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FRONT_THREADS) k_finish_dims(
+    long long n, const cwq_segment* __restrict__ segs, int n_seg, int T, const float* __restrict__ q_loc,
+    const float* __restrict__ q_scale, const float* __restrict__ p_loc, const float* __restrict__ p_scale,
+    const uint8_t* __restrict__ mask, const long long* __restrict__ starts, const uint32_t* __restrict__ gseed,
+    const int* __restrict__ gid, const uint32_t* __restrict__ index, const uint32_t* __restrict__ tile_out_off,
+    float* __restrict__ sample, long long* __restrict__ outlier_idx, uint16_t* __restrict__ outlier_q,
+    long long* __restrict__ seg_outlier_off, const uint32_t* __restrict__ base, const long long* __restrict__ ng_dev,
+    long long n_tiles, ull* __restrict__ pack_words, const int* __restrict__ tile_segment) {
+  __shared__ uint32_t sm_scan[33];
+  __shared__ ull sm_bits[33];
   const int tid = threadIdx.x;
-  if (tid == 0) s_tile = (long long)atomicAdd(&scalars[FRONT_TICKET_PACK], 1ull);
-  __syncthreads();
-  const long long t = s_tile;
-  const long long ng = ng_dev ? *ng_dev : n_groups_cap;
-  const long long g0 = t * PACK_TILE + (long long)tid * PACK_ITEMS;
-  ull pat[PACK_ITEMS];
-  int len[PACK_ITEMS];
-  ull mine = 0;
-#pragma unroll
-  for (int r = 0; r < PACK_ITEMS; ++r) {
-    len[r] = 0;
-    pat[r] = 0;
-    if (g0 + r < ng) {
-      elias_delta_bits(index[g0 + r] + 1u, pat[r], len[r]);
-      mine += (ull)len[r];
+  const long long t = blockIdx.x;
+  {
+    // code bits of the groups that START in this tile, published for the packing kernel that follows on the stream
+    const long long g0 = base[t], g1 = t + 1 < n_tiles ? (long long)base[t + 1] : *ng_dev;
+    ull bits = 0;
+    for (long long g = g0 + tid; g < g1; g += FRONT_THREADS) {
+      ull pat; int len;
+      elias_delta_bits(index[g] + 1u, pat, len);
+      bits += (ull)len;
+    }
+    ull tot_bits;
+    block_exclusive_scan<ull>(bits, sm_bits, tot_bits);
+    if (tid == 0) {
+      const TilePrefix<1> tp = TilePrefix<1>::carve(pack_words, n_tiles);
+      const ull agg[1] = {tot_bits};
+      tp.publish(t, agg);
     }
   }
-  ull tot;
-  ull pre = block_exclusive_scan<ull>(mine, sm_scan, tot);
-  if (tid < 32) {
-    const ull e = lookback_exclusive(status, t, tot);
-    if (tid == 0) s_excl = e;
-  }
-  __syncthreads();
-  pre += s_excl;
-#pragma unroll
-  for (int r = 0; r < PACK_ITEMS; ++r) {
-    if (g0 + r < ng) {
-      bit_off[g0 + r] = (long long)pre;
-      put_bits_bytes(words, pre, pat[r], len[r]);
-      pre += (ull)len[r];
-      if (g0 + r == ng - 1) bit_off[ng] = (long long)pre;
+  const long long tile0 = t * T;
+  const long long tile_end = tile0 + T < n ? tile0 + T : n;
+  const int D = T / FRONT_THREADS;
+  const long long i0 = tile0 + (long long)tid * D;
+  // D consecutive dims per thread, in chunks of 4 (vector loads / stores); the Philox block of a quad is computed once for
+  // the dims of the thread that share it
+  const bool aligned = (((uintptr_t)p_loc | (uintptr_t)p_scale | (uintptr_t)sample | (uintptr_t)gid) & 15u) == 0 &&
+                       ((uintptr_t)mask & 3u) == 0;     // caller-owned buffers: vector access only when it is legal
+  uint32_t my_out = 0;
+  for (int c = 0; c < D; c += 4) {
+    const long long i = i0 + c;
+    if (aligned && i + 4 <= tile_end) {
+      const uint32_t m4 = *reinterpret_cast<const uint32_t*>(mask + i);
+      my_out += __popc(m4 & 0x02020202u);
+    } else {
+      for (int r = 0; r < 4; ++r)
+        if (i + r < tile_end) my_out += (mask[i + r] >> 1) & 1u;
     }
   }
+  uint32_t tot;
+  uint32_t pre = block_exclusive_scan<uint32_t>(my_out, sm_scan, tot) + tile_out_off[t];
+  int last_g = -1;
+  uint32_t last_q = 0;
+  float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int c = 0; c < D; c += 4) {
+    const long long ic = i0 + c;
+    if (ic >= tile_end) break;
+    const bool vec = aligned && ic + 4 <= tile_end;
+    uint32_t m4 = 0;
+    int4 gv = make_int4(0, 0, 0, 0);
+    float4 plv = make_float4(0.f, 0.f, 0.f, 0.f), psv = plv;
+    if (vec) {
+      m4 = *reinterpret_cast<const uint32_t*>(mask + ic);
+      gv = *reinterpret_cast<const int4*>(gid + ic);
+      plv = *reinterpret_cast<const float4*>(p_loc + ic);
+      psv = *reinterpret_cast<const float4*>(p_scale + ic);
+    }
+    float out4[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long i = ic + r;
+      if (!vec && i >= tile_end) { out4[r] = 0.0f; continue; }
+      const uint8_t mm = vec ? (uint8_t)(m4 >> (8 * r)) : mask[i];
+      int s = -1;
+      if (mm & 6) s = segment_of(segs, n_seg, tile_segment, i);
+      if (mm & 4) seg_outlier_off[s] = (long long)pre;       // outliers before this segment
+      if (mm & 2) {
+        const long long local = i - segs[s].start;
+        float zo[4];
+        normal_quad(segs[s].seed + OUTLIER_STREAM_OFFSET, (uint32_t)local, 0u, zo);
+        const float v = __fadd_rn(__fmul_rn(q_scale[i], zo[0]), q_loc[i]);
+        const uint16_t qv = quantize_u16(v);
+        out4[r] = dequantize_u16(qv);
+        outlier_idx[pre] = local;
+        outlier_q[pre] = qv;
+        ++pre;
+      } else {
+        const int g = vec ? (r == 0 ? gv.x : r == 1 ? gv.y : r == 2 ? gv.z : gv.w) : gid[i];
+        const uint32_t d = (uint32_t)(i - starts[g]);
+        if (g != last_g || (d >> 2) != last_q) {
+          normal_quad(gseed[g], index[g], d >> 2, z);
+          last_g = g;
+          last_q = d >> 2;
+        }
+        const float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
+        const float ps = vec ? (r == 0 ? psv.x : r == 1 ? psv.y : r == 2 ? psv.z : psv.w) : p_scale[i];
+        const float pl = vec ? (r == 0 ? plv.x : r == 1 ? plv.y : r == 2 ? plv.z : plv.w) : p_loc[i];
+        out4[r] = __fadd_rn(__fmul_rn(ps, zz), pl);
+      }
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(sample + ic) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (ic + r < tile_end) sample[ic + r] = out4[r];
+    }
+  }
+}
+
+// Elias-delta bitstream (CIS:258-260): every dim tile packs the codes of the groups that start in it; bit offsets from the
+// tile aggregates k_finish_dims published (nothing waits), atomicOr of byte-swapped words into the zeroed stream
+__global__ void __launch_bounds__(FRONT_THREADS) k_pack_elias(const uint32_t* __restrict__ index, const uint32_t* __restrict__ base,
+                                                              const long long* __restrict__ ng_dev, long long n_tiles,
+                                                              uint32_t* __restrict__ words, long long* __restrict__ bit_off,
+                                                              ull* __restrict__ pack_words) {
+  __shared__ ull sm_scan[33];
+  const int tid = threadIdx.x;
+  const long long t = blockIdx.x;
+  const TilePrefix<1> tp = TilePrefix<1>::carve(pack_words, n_tiles);
+  ull excl[1];
+  tp.exclusive(t, sm_scan, excl);
+  ull running = excl[0];
+  const long long ng = *ng_dev;
+  const long long g0 = base[t], g1 = t + 1 < n_tiles ? (long long)base[t + 1] : ng;
+  for (long long c = g0; c < g1; c += FRONT_THREADS) {
+    const long long g = c + tid;
+    ull pat = 0;
+    int len = 0;
+    if (g < g1) elias_delta_bits(index[g] + 1u, pat, len);
+    ull tot;
+    const ull pre = running + block_exclusive_scan<ull>((ull)len, sm_scan, tot);
+    if (g < g1) {
+      bit_off[g] = (long long)pre;
+      put_bits_bytes(words, pre, pat, len);
+    }
+    running += tot;
+  }
+  if (t == n_tiles - 1 && tid == 0) bit_off[ng] = (long long)running;
 }
 
 }  // namespace cwq
@@ -546,7 +642,7 @@ bool front_plan(long long n, long long max_group_size, FrontPlan* p) {
     const size_t smem_tiles = (size_t)(T + E) * 4 + (size_t)E * (T / 32) * 4 + (size_t)T + 64;
     if (smem_chain <= 200 * 1024 && smem_tiles <= 160 * 1024) {
       p->T = T; p->E = E; p->W = T / 32; p->n_tiles = nt;
-      p->smem_tiles = smem_tiles; p->smem_chain = smem_chain; p->smem_groups = (size_t)4 * (T / 32) * 4;
+      p->smem_tiles = smem_tiles; p->smem_chain = smem_chain; p->smem_groups = (size_t)(T + E) * 4 + (size_t)4 * (T / 32) * 4 + (size_t)T;
       return true;
     }
   }
@@ -559,7 +655,7 @@ size_t front_workspace_bytes(long long n, int n_seg, long long cap, const FrontP
   b += align_up((size_t)cap * 8);                           // keys
   b += align_up((size_t)p.n_tiles * 4);                     // tile_out_off
   b += align_up(64);                                        // scalars
-  b += align_up((size_t)((cap + PACK_TILE - 1) / PACK_TILE) * 8);   // look-back words of the packing kernel
+  b += align_up(TilePrefix<1>::words(p.n_tiles) * 8);       // tile-prefix words of the packing kernel
   b += align_up((size_t)n);                                 // hop
   b += align_up((size_t)n_seg * 4);                         // seg_first
   b += align_up((size_t)p.n_tiles * p.E);                   // maps
@@ -567,7 +663,7 @@ size_t front_workspace_bytes(long long n, int n_seg, long long cap, const FrontP
   b += align_up((size_t)p.n_tiles * p.E * p.W * 4);         // rows
   b += align_up((size_t)p.n_tiles * 4) * 2;                 // tile_out, base
   b += align_up((size_t)p.n_tiles);                         // entry
-  b += align_up((size_t)p.n_tiles * 8 * 2);                 // look-back words of the group kernel (units, work)
+  b += align_up(TilePrefix<2>::words(p.n_tiles) * 8);       // tile-prefix words of the group kernel (units, work)
   return b + 1024;
 }
 
@@ -578,7 +674,7 @@ bool front_carve(void* workspace, size_t bytes, long long n, int n_seg, long lon
   w->keys = ws.take<ull>((size_t)cap);
   w->tile_out_off = ws.take<uint32_t>((size_t)p.n_tiles);
   w->scalars = ws.take<ull>(8);
-  w->pack_status = ws.take<ull>((size_t)((cap + PACK_TILE - 1) / PACK_TILE));
+  w->pack_status = ws.take<ull>(TilePrefix<1>::words(p.n_tiles));
   w->hop = ws.take<uint8_t>((size_t)n);
   w->seg_first = ws.take<int>((size_t)n_seg);
   w->maps = ws.take<uint8_t>((size_t)p.n_tiles * p.E);
@@ -587,7 +683,7 @@ bool front_carve(void* workspace, size_t bytes, long long n, int n_seg, long lon
   w->tile_out = ws.take<uint32_t>((size_t)p.n_tiles);
   w->base = ws.take<uint32_t>((size_t)p.n_tiles);
   w->entry = ws.take<uint8_t>((size_t)p.n_tiles);
-  w->status = ws.take<ull>((size_t)p.n_tiles * 2);
+  w->status = ws.take<ull>(TilePrefix<2>::words(p.n_tiles));
   return w->status != nullptr;
 }
 
@@ -596,35 +692,55 @@ int front_group(const float* q_loc, const float* q_scale, const float* p_loc, co
                 cudaStream_t st) {
   if (p.smem_tiles > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_front_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_tiles));
   if (p.smem_chain > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_front_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_chain));
+  if (p.smem_groups > 48 * 1024) CWQ_CUDA(cudaFuncSetAttribute(k_front_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_groups));
+  const int* ts = b->tile_segment;
+  const long long* ng_dev = (const long long*)b->seg_group_off + n_seg;
+  int slot = trace_begin(TR_FRONT_TILES, st);
   k_front_tiles<<<(unsigned)p.n_tiles, FRONT_THREADS, p.smem_tiles, st>>>(
       q_loc, q_scale, p_loc, p_scale, n, segs, n_seg, p.T, p.E, b->kl, (float2*)b->coef, b->mask, w.hop, w.seg_first, w.maps,
-      w.counts, w.rows, w.tile_out);
+      w.counts, w.rows, w.tile_out, ts);
   CWQ_LAUNCH_CHECK();
+  trace_end(slot, st);
+  slot = trace_begin(TR_FRONT_CHAIN, st);
   k_front_chain<<<1, CHAIN_THREADS, p.smem_chain, st>>>(n, segs, n_seg, p.T, p.E, p.n_tiles, w.seg_first, w.maps, w.counts, w.rows,
                                                        w.tile_out, w.entry, w.base, w.tile_out_off, (long long*)b->starts,
                                                        (long long*)b->seg_group_off, (long long*)b->seg_outlier_off, w.status,
                                                        w.scalars);
   CWQ_LAUNCH_CHECK();
+  trace_end(slot, st);
+  slot = trace_begin(TR_FRONT_GROUPS, st);
   k_front_groups<<<(unsigned)p.n_tiles, FRONT_THREADS, p.smem_groups, st>>>(
       n, segs, n_seg, p.T, p.E, p.n_tiles, b->kl, w.hop, w.seg_first, w.rows, w.entry, w.base, (const long long*)b->seg_group_off,
-      (long long*)b->starts, b->gid, b->group_seed, b->total_kl, b->K, w.keys, w.unit_off, w.work_off, w.status, w.scalars);
+      (long long*)b->starts, b->gid, b->group_seed, b->total_kl, b->K, w.keys, w.unit_off, w.work_off, w.status, ts);
   CWQ_LAUNCH_CHECK();
+  trace_end(slot, st);
+  slot = trace_begin(TR_FRONT_PREFIX, st);
+  k_front_prefix<<<(unsigned)p.n_tiles, PREFIX_THREADS, 0, st>>>(p.n_tiles, w.base, ng_dev, w.unit_off, w.work_off, w.status);
+  CWQ_LAUNCH_CHECK();
+  trace_end(slot, st);
   return CWQ_OK;
 }
 
 int front_finish(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale, long long n,
                  const cwq_segment* segs, int n_seg, long long cap, const FrontPlan& p, const FrontWorkspace& w,
                  const cwq_is_buffers* b, cudaStream_t st) {
-  const long long pack_tiles = (cap + PACK_TILE - 1) / PACK_TILE;
+  (void)cap;
+  const long long* ng_dev = (const long long*)b->seg_group_off + n_seg;
   CWQ_CUDA(cudaMemsetAsync(b->bits, 0, b->bits_capacity_bytes, st));
+  CWQ_CUDA(cudaMemsetAsync(w.pack_status, 0, TilePrefix<1>::words(p.n_tiles) * 8, st));
+  int slot = trace_begin(TR_FINISH_DIMS, st);
   k_finish_dims<<<(unsigned)p.n_tiles, FRONT_THREADS, 0, st>>>(n, segs, n_seg, p.T, q_loc, q_scale, p_loc, p_scale, b->mask,
                                                               (const long long*)b->starts, b->group_seed, b->gid, b->index,
                                                               w.tile_out_off, b->sample, (long long*)b->outlier_idx, b->outlier_q,
-                                                              (long long*)b->seg_outlier_off, w.pack_status, pack_tiles, w.scalars);
+                                                              (long long*)b->seg_outlier_off, w.base, ng_dev, p.n_tiles,
+                                                              w.pack_status, b->tile_segment);
   CWQ_LAUNCH_CHECK();
-  k_pack_elias<<<(unsigned)pack_tiles, FRONT_THREADS, 0, st>>>(b->index, cap, (const long long*)b->seg_group_off + n_seg,
-                                                              (uint32_t*)b->bits, (long long*)b->bit_off, w.pack_status, w.scalars);
+  trace_end(slot, st);
+  slot = trace_begin(TR_PACK, st);
+  k_pack_elias<<<(unsigned)p.n_tiles, FRONT_THREADS, 0, st>>>(b->index, w.base, ng_dev, p.n_tiles, (uint32_t*)b->bits,
+                                                             (long long*)b->bit_off, w.pack_status);
   CWQ_LAUNCH_CHECK();
+  trace_end(slot, st);
   return CWQ_OK;
 }
 

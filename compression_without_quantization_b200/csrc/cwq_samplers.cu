@@ -704,11 +704,23 @@ static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // optional timing of the dominant kernel (k_is_score) with CUDA events on the launching stream
-constexpr int PROFILE_RING = 256;
-static bool g_profile = false;
+constexpr int PROFILE_RING = 1024;
+static int g_profile = 0;        // 0 off, 1 scoring kernel only, 2 every kernel of the fused pipeline
 static cudaEvent_t g_ev0[PROFILE_RING], g_ev1[PROFILE_RING];
+static int g_kind[PROFILE_RING];
 static int g_profile_count = 0;
 static bool g_profile_events_ready = false;
+
+int trace_begin(int kind, cudaStream_t st) {
+  if (!g_profile || (g_profile == 1 && kind != TR_SCORE) || g_profile_count >= PROFILE_RING) return -1;
+  const int slot = g_profile_count++;
+  g_kind[slot] = kind;
+  cudaEventRecord(g_ev0[slot], st);
+  return slot;
+}
+void trace_end(int slot, cudaStream_t st) {
+  if (slot >= 0) cudaEventRecord(g_ev1[slot], st);
+}
 
 static int g_sm_count = 0, g_is_blocks_per_sm = 0, g_is_blocks_per_sm_any = 0;
 static int ensure_device_props() {
@@ -752,11 +764,12 @@ extern "C" int cwq_profile_enable(int on) {
     for (int i = 0; i < PROFILE_RING; ++i) { CWQ_CUDA(cudaEventCreate(&g_ev0[i])); CWQ_CUDA(cudaEventCreate(&g_ev1[i])); }
     g_profile_events_ready = true;
   }
-  g_profile = on != 0;
+  g_profile = on < 0 ? 0 : (on > 2 ? 2 : on);
   g_profile_count = 0;
   return CWQ_OK;
 }
 extern "C" int cwq_profile_count(void) { return g_profile_count; }
+extern "C" int cwq_profile_kind(int i) { return (i >= 0 && i < g_profile_count) ? g_kind[i] : -1; }
 extern "C" int cwq_profile_get_ms(int i, float* ms) {
   CWQ_REQUIRE(i >= 0 && i < g_profile_count && ms, "no such profile record");
   CWQ_CUDA(cudaEventElapsedTime(ms, g_ev0[i], g_ev1[i]));
@@ -803,8 +816,7 @@ static int is_encode_impl(const float* coef, const int64_t* starts, const int32_
     CWQ_LAUNCH_CHECK();
   }
   const int is_global = front ? 1 : 0;
-  const bool prof = g_profile && g_profile_count < PROFILE_RING;
-  if (prof) CWQ_CUDA(cudaEventRecord(g_ev0[g_profile_count], st));
+  const int slot = trace_begin(TR_SCORE, st);
   if (max_group_size <= 16)
     k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
                                                                               group_seed, range, unit_off, is_global, counter, keys);
@@ -812,9 +824,11 @@ static int is_encode_impl(const float* coef, const int64_t* starts, const int32_
     k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
                                                                                    group_seed, range, unit_off, is_global, counter, keys);
   CWQ_LAUNCH_CHECK();
-  if (prof) { CWQ_CUDA(cudaEventRecord(g_ev1[g_profile_count], st)); ++g_profile_count; }
+  trace_end(slot, st);
+  const int slot_i = trace_begin(TR_INDEX, st);
   k_is_index<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(keys, range, index);
   CWQ_LAUNCH_CHECK();
+  trace_end(slot_i, st);
   return CWQ_OK;
 }
 

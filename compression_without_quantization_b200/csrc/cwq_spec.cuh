@@ -66,8 +66,22 @@ __device__ __forceinline__ void mulwide(uint32_t a, uint32_t m, uint32_t& hi, ui
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t STREAM_KEY0 = 0x6A09E667u;     // frac(sqrt 2): a nothing-up-my-sleeve constant
 
+__device__ __forceinline__ void mulwide(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo);
+
+// one whole block straight from the definition (decode / replay / debug kernels), one IMAD.WIDE per product; round 0's
+// second product is 0 * M1 = 0 (c2 = 0)
 __device__ __forceinline__ void stream_block(uint32_t sseed, uint32_t k, uint32_t j, uint32_t (&o)[4]) {
-  philox4x32_10(sseed, k, 0u, j, STREAM_KEY0, STREAM_KEY1, o);
+  uint32_t c0 = sseed, c1 = k, c2 = 0u, c3 = j;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, l0, h1, l1;
+    mulwide(c0, PHILOX_M0, h0, l0);
+    if (r == 0) { h1 = 0u; l1 = 0u; } else mulwide(c2, PHILOX_M1, h1, l1);
+    const uint32_t n0 = h1 ^ c1 ^ (STREAM_KEY0 + (uint32_t)r * PHILOX_W0);
+    const uint32_t n2 = h0 ^ c3 ^ (STREAM_KEY1 + (uint32_t)r * PHILOX_W1);
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
 // number of Philox blocks a row of nq quads (4 dims each) needs: 3 per full unit, min(rest, 3) for the tail

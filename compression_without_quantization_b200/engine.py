@@ -162,7 +162,14 @@ class SegmentTable:
             off += sp.n
         self.n = off
         self.starts = [int(s.start) for s in self.host]
-        self.dev = _segment_table_on_device(bytes(self.host), torch.device(device))
+        # behind the table, in the same upload: the segment of every dim 1024 k (cwq_is_buffers.tile_segment), which lets
+        # the fused kernels find a dim's segment with one load instead of a binary search at kernel start
+        seg_bytes = bytes(self.host)
+        pad = (-len(seg_bytes)) % 16
+        tile_seg = (np.searchsorted(np.asarray(self.starts, dtype=np.int64), np.arange(0, off, 1024, dtype=np.int64),
+                                    side="right") - 1).astype(np.int32)
+        self.dev = _segment_table_on_device(seg_bytes + b"\0" * pad + tile_seg.tobytes(), torch.device(device))
+        self.tile_segment_ptr = self.dev.data_ptr() + len(seg_bytes) + pad
         self.max_size_limit = max(int(s.size_limit) for s in self.host)
 
 
@@ -373,6 +380,7 @@ class ISJob:
         buf.bits_capacity_bytes = bits_cap
         buf.workspace_bytes = wsb
         buf.score_range_dev = None
+        buf.tile_segment = self.table.tile_segment_ptr
         self._buffers = buf
         for name in ("kl", "coef", "mask", "total_kl", "K", "index", "sample", "outlier_idx", "outlier_q", "seg_outlier_off",
                      "bits", "bit_off"):

@@ -64,8 +64,11 @@ CWQ_API int cwq_device_info(int device, int* sm_count, int* cc_major, int* cc_mi
 CWQ_API long long cwq_launch_count(void);
 /* CUDA-event timing of the dominant kernel (the importance-sampler scoring kernel) on its launching
  * stream: enable, run, synchronise, then read up to 256 records. */
-CWQ_API int cwq_profile_enable(int on);
+CWQ_API int cwq_profile_enable(int on);   /* 0 off, 1 the scoring kernel, 2 every kernel of cwq_is_encode_pipeline */
 CWQ_API int cwq_profile_count(void);
+/* what record i timed: 0 scoring kernel, 1 tiles (prologue + boundaries), 2 chain, 3 groups, 4 unit/work prefix, 5 index
+ * extraction, 6 decode + outliers, 7 Elias-delta packing; -1 no such record */
+CWQ_API int cwq_profile_kind(int i);
 CWQ_API int cwq_profile_get_ms(int i, float* ms);
 
 /* ---- per-dim prologue ------------------------------------------------------------------------
@@ -174,6 +177,9 @@ typedef struct cwq_is_buffers {
   size_t workspace_bytes;
   const int64_t* score_range_dev; /* NULL: the SCORE stage covers all groups; else two int64 on the device, the range
                                      [g0, g1) of groups this rank scores (sharded runs: cwq_is_pipeline_shard_ranges) */
+  const int32_t* tile_segment;    /* NULL, or [ceil(n / 1024)] on the device: index of the segment that holds dim 1024 k.
+                                     A hint only (results do not depend on it): the kernels then find a dim's segment with
+                                     one load instead of a binary search over the segment table */
 } cwq_is_buffers;
 CWQ_API size_t cwq_is_pipeline_workspace_bytes(int64_t n, int32_t n_segments, int64_t max_group_size);
 /* Contiguous work-balanced ranges of groups for `world` ranks (same cut rule as cwq_is_shard_ranges), computed on the
