@@ -144,36 +144,49 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
 
 
 def _segment_result(job, s, host, return_indices):
+    """What the reference call of segment s returns, cut out of the host copies (which cover the calls host["calls"])."""
     g0, g1 = job.segment_group_range(s)
     a, b = job.table.starts[s], job.table.starts[s] + job.table.specs[s].n
-    sample = host["sample"][a:b]
-    starts = host["starts"][g0:g1 + 1] - a
-    o0, o1 = int(host["seg_outlier_off"][s]), int(host["seg_outlier_off"][s + 1])
+    d0, gb, o_base, bit_base = host["dim0"], host["group0"], host["outlier0"], host["bit0"]
+    sample = host["sample"][a - d0:b - d0]
+    starts = host["starts"][g0 - gb:g1 + 1 - gb] - a
+    o0, o1 = int(host["seg_outlier_off"][s]) - o_base, int(host["seg_outlier_off"][s + 1]) - o_base
     outlier_extras = (host["outlier_idx"][o0:o1], host["outlier_q"][o0:o1])
     if return_indices:
-        indices = [np.int64(i) + 1 for i in host["index"][g0:g1]]
+        indices = [np.int64(i) + 1 for i in host["index"][g0 - gb:g1 - gb]]
         return sample, indices, starts, outlier_extras
-    bit0, bit1 = int(host["bit_off"][g0]), int(host["bit_off"][g1])
+    bit0, bit1 = int(host["bit_off"][g0 - gb]) - bit_base, int(host["bit_off"][g1 - gb]) - bit_base
     bitcode = host["ascii"][bit0:bit1].tobytes()
     return sample, bitcode, starts, outlier_extras
 
 
-def _host_views(job, with_bits):
-    """One batch of device->host copies for everything the caller gets back."""
-    ng = job.groups.n_groups
-    counts = [job.seg_outlier_off[-1:]] + ([job.bit_off[ng:ng + 1]] if with_bits else [])
-    counts = [int(c[0]) for c in E.to_host(counts)]          # copies only: no kernel on this stream
-    n_out, total_bits = counts[0], (counts[1] if with_bits else 0)
-    names = ["sample", "starts", "index", "outlier_idx", "outlier_q", "seg_outlier_off"]
-    tensors = [job.sample, job.groups.starts, job.index, job.outlier_idx[:n_out], job.outlier_q[:n_out], job.seg_outlier_off]
+def _host_views(job, with_bits, calls=None):
+    """Device->host copies of everything the caller gets back for the calls [calls[0], calls[1]) of the job (default: all):
+    one small copy for the counts, then one batch of copies for the payload.  No kernel runs on this stream unless the
+    '0'/'1' expansion has not been queued yet."""
+    s0, s1 = (0, job.table.count) if calls is None else calls
+    g0, g1 = job.segment_group_range(s0)[0], job.segment_group_range(s1 - 1)[1]
+    d0, d1 = job.table.starts[s0], job.table.starts[s1 - 1] + job.table.specs[s1 - 1].n
+    small = [job.seg_outlier_off] + ([job.bit_off[g0:g0 + 1], job.bit_off[g1:g1 + 1]] if with_bits else [])
+    small = E.to_host(small)                                 # copies only
+    seg_out = small[0].copy()
+    o0, o1 = int(seg_out[s0]), int(seg_out[s1])
+    bit0, bit1 = (int(small[1][0]), int(small[2][0])) if with_bits else (0, 0)
+    names = ["sample", "starts", "index", "outlier_idx", "outlier_q"]
+    tensors = [job.sample[d0:d1], job.groups.starts[g0:g1 + 1], job.index[g0:g1], job.outlier_idx[o0:o1], job.outlier_q[o0:o1]]
     if with_bits:
         # packed bits -> the reference's '0'/'1' characters on the device, once for the whole batch
         names += ["bit_off", "ascii"]
-        ascii_dev = job.ascii[:total_bits] if hasattr(job, "ascii") else E.device_bits_to_ascii(job.bits, total_bits)
-        tensors += [job.bit_off, ascii_dev]
+        if hasattr(job, "ascii"):
+            ascii_dev = job.ascii[bit0:bit1]
+        else:
+            total = int(E.to_host([job.bit_off[job.groups.n_groups:job.groups.n_groups + 1]])[0][0])
+            ascii_dev = E.device_bits_to_ascii(job.bits, total)[bit0:bit1]
+        tensors += [job.bit_off[g0:g1 + 1], ascii_dev]
     host = dict(zip(names, E.to_host(tensors)))
     host["index"] = host["index"].view(np.uint32)
     host["outlier_q"] = host["outlier_q"].view(np.uint16)
+    host.update(seg_outlier_off=seg_out, dim0=d0, group0=g0, outlier0=o0, bit0=bit0, calls=(s0, s1))
     return host
 
 
@@ -230,11 +243,21 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
     up, down, peek = _copy_streams(dev)
     up.wait_stream(compute)
     staged = []
+    # a sharded run: every rank uploads 1/world of each chunk and the ranks all-gather the rest over NVLink; every rank
+    # collects (downloads + formats) the results of its own calls only, unless the shard asks for all of them
+    own = (0, len(specs))
+    sliced = False
+    if shard is not None and hasattr(shard, "call_range"):
+        own = shard.call_range([sp.n for sp in specs])
+        sliced = shard.can_slice_uploads(targets, proposals)
 
     def upload(i):                                   # stage 1: a chunk's inputs on the copy stream
         a, b = chunks[i]
         with torch.cuda.stream(up):
-            tensors = _upload(targets[a:b], proposals[a:b], dev)
+            if sliced:
+                tensors = shard.upload_sliced(targets[a:b], proposals[a:b], dev)
+            else:
+                tensors = _upload(targets[a:b], proposals[a:b], dev)
             ev = torch.cuda.Event()
             ev.record(up)
         staged.append((tensors, ev))
@@ -276,10 +299,15 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
 
     def collect(i):                                  # stage 3: download (copies only) + formatting while later chunks are scored
         job = jobs[i]
-        down.wait_event(done[i])
-        with torch.cuda.stream(down):
-            host = _host_views(job, with_bits=not return_indices)
-        results[i] = [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+        a, b = chunks[i]
+        lo, hi = max(own[0], a) - a, min(own[1], b) - a          # this rank's calls inside the chunk
+        results[i] = [None] * (b - a)
+        if hi > lo:
+            down.wait_event(done[i])
+            with torch.cuda.stream(down):
+                host = _host_views(job, with_bits=not return_indices, calls=(lo, hi))
+            for s in range(lo, hi):
+                results[i][s] = _segment_result(job, s, host, return_indices)
         jobs[i] = None
 
     # Order on the compute stream: G0 S0 | G1 F0 S1 | G2 F1 S2 | ... : the grouping of the next chunk is queued behind the

@@ -292,16 +292,20 @@ struct PrologueDim { float kl; float2 coef; uint8_t m; };
 __device__ __forceinline__ PrologueDim is_prologue_dim(float ql, float qs, float pl, float ps, float limit);
 
 __device__ __forceinline__ PrologueDim is_prologue_dim(float ql, float qs, float pl, float ps, float limit) {
-  float tl = __fdiv_rn(__fsub_rn(ql, pl), ps);
-  float ts = __fdiv_rn(qs, ps);
-  const float kl_bits = __fdiv_rn(kl01(tl, ts), LN2_F);
+  const float tl = __fdiv_rn(__fsub_rn(ql, pl), ps);
+  const float ts = __fdiv_rn(qs, ps);
+  const float k0 = kl01(tl, ts);
+  const float kl_bits = __fdiv_rn(k0, LN2_F);
   PrologueDim r;
   r.m = 0;
-  if (!(kl_bits <= limit)) { r.m |= 1; tl = 0.0f; ts = 1.0f; }
+  if (!(kl_bits <= limit)) r.m |= 1;
   if (kl_bits > limit) r.m |= 2;
-  r.kl = kl01(tl, ts);
+  // a dim replaced by the prior is N(0, 1) against N(0, 1): kl01(0, 1) and both coefficients are exactly +0, so the
+  // replaced branch is a select, not a second evaluation (same bits as evaluating the formulas at (0, 1))
   const float iv = __fdiv_rn(1.0f, __fmul_rn(ts, ts));
-  r.coef = make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
+  const bool rep = (r.m & 1) != 0;
+  r.kl = rep ? 0.0f : k0;
+  r.coef = rep ? make_float2(0.0f, 0.0f) : make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
   return r;
 }
 

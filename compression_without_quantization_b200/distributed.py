@@ -83,8 +83,49 @@ class ISShard:
     `shard(job)` runs the three in order.  Jobs whose group tables are already on the host (and the CPU stand-ins of the
     gloo tests) take the plain path: ranges from the host-side tables, then the same encode and all-gather."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, results="own", slice_uploads=True):
+        """results: "own" -- the batch API returns, on every rank, the results of this rank's calls (a contiguous run of
+        calls balanced on dims) and None for the others, so that download and formatting are sharded too; "all" -- every
+        rank downloads and formats everything.  slice_uploads: with host inputs every rank uploads 1/world of each array
+        and the ranks all-gather the rest over NVLink instead of every rank pulling the whole batch over PCIe."""
         self.group = group
+        self.results = results
+        self.slice_uploads = slice_uploads
+
+    def call_range(self, sizes):
+        """[first, last + 1) of the calls whose results this rank returns."""
+        world, rank = self._world_rank()
+        if self.results != "own" or world == 1:
+            return 0, len(sizes)
+        b = balanced_ranges(torch.as_tensor(np.asarray(sizes, dtype=np.int64)), world)
+        return b[rank], b[rank + 1]
+
+    def can_slice_uploads(self, targets, proposals):
+        world, _ = self._world_rank()
+        if not self.slice_uploads or world == 1:
+            return False
+        arrays = [t.loc for t in targets] + [t.scale for t in targets] + [p.loc for p in proposals] + [p.scale for p in proposals]
+        return all((isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.float32) or
+                   (isinstance(a, np.ndarray) and a.dtype == np.float32) for a in arrays)
+
+    def upload_sliced(self, targets, proposals, dev):
+        """The four flat input arrays of a run of calls on the device: this rank copies its 1/world slice from the host,
+        one in-place all-gather per array brings the other ranks' slices (the receive buffer IS the array)."""
+        from . import engine as E
+        world, rank = self._world_rank()
+        out = []
+        lists = ([t.loc for t in targets], [t.scale for t in targets], [p.loc for p in proposals], [p.scale for p in proposals])
+        for arrays in lists:
+            span = E.host_span(arrays)
+            n = int(span.numel())
+            m = (n + world - 1) // world
+            full = torch.empty(world * m, dtype=torch.float32, device=dev)
+            lo, hi = min(n, rank * m), min(n, rank * m + m)
+            if hi > lo:
+                full[lo:hi].copy_(span[lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(full, full[rank * m:rank * m + m], group=self.group)
+            out.append(full[:n])
+        return tuple(out)
 
     def _world_rank(self):
         if dist.is_initialized():
@@ -142,10 +183,10 @@ class ISShard:
         self._all_gather(job, self.finish_plan(job))
 
 
-def make_is_shard(group=None):
-    """`shard` object for code_grouped_importance_sample_batch: encode this rank's range, then one NCCL all-gather of
-    the per-group indices."""
-    return ISShard(group)
+def make_is_shard(group=None, results="own", slice_uploads=True):
+    """`shard` object for code_grouped_importance_sample_batch: encode this rank's range of groups, then one NCCL
+    all-gather of the per-group indices (see ISShard for `results` and `slice_uploads`)."""
+    return ISShard(group, results, slice_uploads)
 
 
 def make_greedy_shard(group=None):

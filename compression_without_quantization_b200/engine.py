@@ -74,6 +74,24 @@ def as_device_f32(x, device=None, what="array"):
     return t.to(device, non_blocking=True).reshape(-1).contiguous()
 
 
+def host_span(arrays):
+    """One flat contiguous float32 CPU tensor holding the concatenation of `arrays` (CPU tensors / numpy): a view when they
+    are consecutive pieces of one buffer (a batch sliced into per-call pieces), else a copy."""
+    ts = [a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)) for a in arrays]
+    ts = [t.reshape(-1) for t in ts]
+    if len(ts) == 1:
+        return ts[0].contiguous()
+    first, pos, adjacent = ts[0], ts[0].data_ptr(), all(t.is_contiguous() for t in ts)
+    for t in ts:
+        if not adjacent or t.data_ptr() != pos or t.untyped_storage().data_ptr() != first.untyped_storage().data_ptr():
+            adjacent = False
+            break
+        pos += t.numel() * 4
+    if adjacent:
+        return torch.as_strided(first, (sum(int(t.numel()) for t in ts),), (1,))
+    return torch.cat(ts)
+
+
 def concat_to_device(arrays, device=None, what="array"):
     """Concatenation of flat float32 arrays on the device.  When the inputs are consecutive views of one host
     buffer (a batch sliced into per-call pieces, as bench.py and pln-style callers produce) the whole span

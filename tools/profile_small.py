@@ -75,6 +75,13 @@ def run(name, arrays, specs, steps=40):
 
 def main():
     n1, n2 = pln_level_sizes(512, 768)
+    if "--batch" in sys.argv:
+        arrays, specs = [], []
+        for img in range(24):
+            arrays += [synthetic_posterior(n2, 1000 + img), synthetic_posterior(n1, img)]
+            specs += [E.SegmentSpec(n2, 42, 20, 2, 16, True), E.SegmentSpec(n1, 42, 20, 4, 16, True)]
+        run("configs[3]: 24 x (768x512), IS 20 bits", arrays, specs, steps=5)
+        return
     run("configs[1]: one 768x512 image, IS 20 bits", [synthetic_posterior(n2, 1000), synthetic_posterior(n1, 0)],
         [E.SegmentSpec(n2, 42, 20, 2, 16, True), E.SegmentSpec(n1, 42, 20, 4, 16, True)])
     for bits in (8, 12, 16):
