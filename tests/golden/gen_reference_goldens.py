@@ -104,6 +104,47 @@ for name, n, key, nontrivial, seed, steps, b, m in GR_CASES:
                 name + "_starts": np.asarray(starts, np.int64), name + "_decoded": np.asarray(decoded, np.float32)})
     print(name, "groups", len(starts) - 1, "bits", len(bitcode))
 
+# ---- the reference's DEFAULT sizes (miracle_arguments.py:147-190): a 20-bit importance-sampler budget with 16-dim groups
+# (K up to 385 751 candidates, CIS:48-51) and a greedy group of ~500 dims at 30 steps x 2^14 candidates (CGS:51-78) ----
+def default_size_cases():
+    f = np.float32
+    rng = np.random.default_rng(9100)
+    n = 40                                            # 16 + 16 + 7 + the last dim on its own
+    q_scale = np.full(n, 0.3) * np.exp(0.05 * rng.normal(size=n))
+    q_loc = 0.15 * rng.normal(size=n)                 # ~0.75 nats per dim: a 16-dim group holds ~12 nats, K ~ 1.6e5
+    isd = (q_loc.astype(f), q_scale.astype(f), np.zeros(n, f), np.ones(n, f))
+    grd = posterior(600, 30, False)                   # first group: ~520 dims inside 30 * 14 bits
+    return isd, grd
+
+
+isd_in, grd_in = default_size_cases()
+tf_shim.set_outlier_seed(42)
+with redirect_stdout(sink):
+    target, proposal = tfd.Normal(loc=isd_in[0], scale=isd_in[1]), tfd.Normal(loc=isd_in[2], scale=isd_in[3])
+    sample, bitcode, starts, (o_idx, o_q) = CIS.code_grouped_importance_sample(sess, target, proposal, 42, 20, max_group_size_bits=4,
+                                                                               dim_kl_bit_limit=16)
+    decoded = CIS.decode_grouped_importance_sample(sess, bitcode, [int(x) for x in starts[:-1]], proposal, 20, 42, o_idx, o_q)
+    _, isd_group_kls = CIS.code_grouped_importance_sample(sess, target, proposal, 42, 20, max_group_size_bits=4, dim_kl_bit_limit=16,
+                                                          return_group_indices_only=True)
+t_loc, t_scale, kl = O.greedy_prologue(*[isd_in[k] for k in (0, 1, 2, 3)])
+tot, Ks = O.group_totals(kl, np.asarray(starts, np.int64))
+assert Ks.max() >= 100000 and len(o_idx) == 0, (Ks, o_idx)
+out.update({"isd_in": np.stack(isd_in), "isd_par": np.array([42, 20, 4, 16]), "isd_sample": np.asarray(sample, np.float32),
+            "isd_bitcode": np.frombuffer(bitcode, np.uint8), "isd_starts": np.asarray(starts, np.int64),
+            "isd_oidx": np.asarray(o_idx, np.int64), "isd_oq": np.asarray(o_q, np.uint16),
+            "isd_decoded": np.asarray(decoded, np.float32), "isd_K": Ks.astype(np.int64),
+            "isd_group_kls": np.asarray(isd_group_kls, np.float64)})
+print("isd groups", len(starts) - 1, "K", list(Ks), "bits", len(bitcode))
+with redirect_stdout(sink):
+    target, proposal = tfd.Normal(loc=grd_in[0], scale=grd_in[1]), tfd.Normal(loc=grd_in[2], scale=grd_in[3])
+    sample, bitcode, starts = CGS.code_grouped_greedy_sample(sess, target, proposal, 30, 14, 42, max_group_size_bits=12)
+    decoded = CGS.decode_grouped_greedy_sample(sess, bitcode, list(starts[:-1]), proposal, 14, 30, 42)
+assert max(np.diff(starts)) >= 400, starts
+out.update({"grd_in": np.stack(grd_in), "grd_par": np.array([42, 30, 14, 12]), "grd_sample": np.asarray(sample, np.float32),
+            "grd_bitcode": np.frombuffer(bitcode.encode(), np.uint8), "grd_starts": np.asarray(starts, np.int64),
+            "grd_decoded": np.asarray(decoded, np.float32)})
+print("grd groups", len(starts) - 1, "sizes", list(np.diff(starts)), "bits", len(bitcode))
+
 # per-group greedy entry points with a non-zero proposal loc (CGS:29-89, 93-167: shard prior N(p_loc / n_steps, ...))
 PG_CASES = [  # name, G, key, seed, n_steps, n_bits_per_step, rho
     ("pg0", 27, 20, 42, 5, 6, 1.0), ("pg1", 5, 21, 7, 2, 7, 0.8), ("pg2", 36, 22, 123, 4, 6, 1.0),

@@ -492,6 +492,52 @@ def test_greedy_batch_equals_separate_calls(cwq, syn):
         assert batch[i][1] == one[1] and batch[i][2] == one[2]
 
 
+def test_default_size_importance_group_bit_exact_with_injected_draws(cwq, oracle, syn):
+    """The reference's default budget: 20 bits, 16-dim groups, K up to 385 751 (CIS:48-51).  Inputs of golden `isd` (two
+    groups with K ~ 1.6e5): engine == oracle fed the engine's draws, bit for bit; and against the golden itself (made by the
+    unmodified reference with libm draws) the group tables and K are equal and indices differ only on near ties."""
+    from compression_without_quantization_b200 import engine as E
+    g = _golden()
+    q_loc, q_scale, p_loc, p_scale = g["isd_in"]
+    got = cwq.code_grouped_importance_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), 42, 20, 4, 16)
+    want = oracle.code_grouped_importance_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), 42, 20, 4, 16,
+                                                 normal_source=_src(cwq))
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[2], g["isd_starts"])
+    assert got[1] == want[1]
+    assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32))
+    job = cwq.code_grouped_importance_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), 42, 20, 4, 16,
+                                             return_indices=True)
+    assert max(job[1]) > 1000                                  # a six-digit candidate table was really searched
+    ng = len(got[2]) - 1
+    mine, _ = E.elias_delta_parse(got[1], ng)
+    ref, _ = E.elias_delta_parse(g["isd_bitcode"].tobytes(), ng)
+    same = np.repeat(mine == ref, np.diff(got[2]))
+    assert np.allclose(got[0][same], g["isd_sample"][same], rtol=REL_TOL, atol=3e-5)
+    dec = cwq.decode_grouped_importance_sample(None, g["isd_bitcode"].tobytes(), [int(x) for x in g["isd_starts"][:-1]],
+                                               syn.Normal(p_loc, p_scale), 20, 42, g["isd_oidx"], g["isd_oq"])
+    assert np.allclose(dec, g["isd_decoded"], rtol=REL_TOL, atol=3e-5)      # decode of the REFERENCE's own bitstream
+
+
+def test_default_size_greedy_group_bit_exact_with_injected_draws(cwq, oracle, syn):
+    """The reference's greedy defaults: 30 steps x 2^14 candidates (miracle_arguments.py:147-190), a 558-dim group (inputs of
+    golden `grd`): engine == oracle fed the engine's draws (30 x 16384 x 558 of them), bit for bit, in both kernel shapes;
+    the engine decodes the REFERENCE's own bitstream to the reference's latents."""
+    from compression_without_quantization_b200 import engine as E
+    g = _golden()
+    q_loc, q_scale, p_loc, p_scale = g["grd_in"]
+    starts = [int(x) for x in g["grd_starts"]]
+    G = starts[1]
+    got = cwq.code_grouped_greedy_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), 30, 14, 42, 12)
+    assert got[2] == starts
+    # the first (558-dim) group through the per-group entry points: oracle with injected draws
+    best, code = cwq.code_greedy_sample(q_loc[:G], q_scale[:G], p_loc[:G], p_scale[:G], 14, 30, 42)
+    obest, ocode = oracle.code_greedy_sample(q_loc[:G], q_scale[:G], p_loc[:G], p_scale[:G], 14, 30, 42, normal_source=_src(cwq))
+    assert code == ocode.encode() and np.array_equal(best.view(np.uint32), obest.view(np.uint32))
+    assert got[1][:30 * 14] == ocode and np.array_equal(got[0][:G].view(np.uint32), best.view(np.uint32))
+    dec = cwq.decode_grouped_greedy_sample(None, g["grd_bitcode"].tobytes().decode(), starts[:-1], syn.Normal(p_loc, p_scale), 14, 30, 42)
+    assert np.allclose(dec, g["grd_decoded"], rtol=REL_TOL, atol=3e-5)
+
+
 @pytest.mark.parametrize("name", ["pg0", "pg1", "pg2"])
 def test_gpu_per_group_greedy_with_proposal_loc_against_reference_goldens(cwq, name):
     g = _golden()

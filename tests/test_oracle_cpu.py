@@ -72,6 +72,48 @@ def test_harvested_quad_is_standard_normal_and_uncorrelated_with_the_direct_quad
     assert np.abs(c[off]).max() < 0.02 and np.abs(c2[off]).max() < 0.02
 
 
+def test_harvested_quad_ks_chi2_and_joint_independence(oracle):
+    """Stream v2 takes the fourth quad of every 16 dims from the TOP BYTES of the three Philox blocks whose low 23 bits
+    give the other twelve dims.  Goodness of fit of the harvested dims (Kolmogorov-Smirnov against N(0,1),
+    chi-square of their 23-bit uniforms and of each harvested byte) and independence of a harvested dim from the three
+    direct dims that share its Philox words (chi-square on 16 x 16 contingency tables of the probability transforms).
+    Fixed seeds: the p-values are constants, the thresholds only have to sit below them."""
+    from scipy import stats
+    n = 200000
+    z = oracle.default_normal_source(11, 0, n, 16).astype(np.float64)
+    words = oracle.quad_words(11, 0, n, 4)                       # [n, 4 quads, 4 words]
+    pvals = {}
+    for d in range(12, 16):
+        pvals["ks%d" % d] = stats.kstest(z[:, d], "norm").pvalue
+    for d in range(0, 12, 5):                                     # a few direct dims as the yardstick
+        pvals["ks%d" % d] = stats.kstest(z[:, d], "norm").pvalue
+    # uniforms of the harvested quad: 23-bit mantissas in 256 equal bins, and each harvested byte on its own
+    h = words[:, 3, :] & 0x7FFFFF
+    for i in range(4):
+        pvals["chi_u%d" % i] = stats.chisquare(np.bincount(h[:, i] >> 15, minlength=256)).pvalue
+        for byte in range(2):
+            pvals["chi_b%d_%d" % (i, byte)] = stats.chisquare(np.bincount((h[:, i] >> (8 * byte)) & 0xFF, minlength=256)).pvalue
+        pvals["chi_b%d_2" % i] = stats.chisquare(np.bincount((h[:, i] >> 16) & 0x7F, minlength=128)).pvalue
+    # joint: harvested dim 12 + j shares words with dims j, 4 + j, 8 + j (same word position in blocks 0, 1, 2)
+    u = stats.norm.cdf(z)
+    bins = np.minimum((u * 16).astype(np.int64), 15)
+    for j in range(4):
+        for other in (j, 4 + j, 8 + j):
+            table = np.zeros((16, 16))
+            np.add.at(table, (bins[:, 12 + j], bins[:, other]), 1)
+            pvals["ind%d_%d" % (12 + j, other)] = stats.chi2_contingency(table)[1]
+    # the word-level version of the same question: top byte against the low 23 bits of the SAME word
+    blocks = oracle.stream_words(11, 0, n, 3)                     # [n, 3 blocks, 4 words]
+    for b in range(3):
+        table = np.zeros((16, 16))
+        np.add.at(table, ((blocks[:, b, 0] >> 28).astype(np.int64), ((blocks[:, b, 0] >> 19) & 0xF).astype(np.int64)), 1)
+        pvals["word%d" % b] = stats.chi2_contingency(table)[1]
+    low = {k: v for k, v in pvals.items() if v < 1e-3}
+    assert not low, low
+    # 41 tests: uniformly distributed p-values put about two below 0.05; a defect would put most of them near 0
+    assert sum(v < 0.05 for v in pvals.values()) <= 6, sorted(pvals.items(), key=lambda kv: kv[1])[:8]
+
+
 def test_deterministic_log_exp_accuracy(oracle):
     rng = np.random.default_rng(0)
     xs = np.exp(rng.uniform(-30, 30, 4000)).astype(np.float32)
@@ -131,7 +173,7 @@ def gold():
     return np.load(os.path.join(GOLD, "reference_samplers.npz"))
 
 
-@pytest.mark.parametrize("name", ["is0", "is1", "is2", "is3", "is4"])
+@pytest.mark.parametrize("name", ["is0", "is1", "is2", "is3", "is4", "isd"])
 def test_importance_sampler_matches_unmodified_reference_run(oracle, gold, name):
     q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
     seed, bits, m, limit = [int(x) for x in gold[name + "_par"]]
@@ -166,18 +208,40 @@ def test_is4_covers_outliers_and_empty_first_group(gold):
     assert list(gold["is4_oidx"]) == [10, 33, 43] and list(gold["is4_starts"][:3]) == [0, 0, 1]
 
 
-@pytest.mark.parametrize("name", ["gr0", "gr1", "gr2"])
+def test_default_size_goldens_are_default_sized(gold):
+    """isd: 20-bit budget, 16-dim groups with K > 1e5 candidates (CIS:48-51); grd: a 558-dim greedy group at 30 x 2^14."""
+    assert list(gold["isd_par"]) == [42, 20, 4, 16] and gold["isd_K"].max() >= 100000
+    assert list(np.diff(gold["isd_starts"])[:2]) == [16, 16]
+    assert list(gold["grd_par"]) == [42, 30, 14, 12] and np.diff(gold["grd_starts"]).max() >= 500
+
+
+@pytest.mark.parametrize("name", ["gr0", "gr1", "gr2", "grd"])
 def test_greedy_sampler_matches_unmodified_reference_run(oracle, gold, name):
     q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
     seed, steps, b, m = [int(x) for x in gold[name + "_par"]]
     s, code, starts = oracle.code_grouped_greedy_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), steps,
                                                         b, seed, m)
     assert starts == [int(x) for x in gold[name + "_starts"]]
-    assert code.encode() == gold[name + "_bitcode"].tobytes()
-    assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6)
+    ref = gold[name + "_bitcode"].tobytes().decode()
     d = oracle.decode_grouped_greedy_sample(None, code, starts[:-1], oracle.Normal(p_loc, p_scale), b, steps, seed)
-    assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(d, s)
+    if name != "grd":
+        assert code == ref
+        assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
+        return
+    # default sizes: the 558- and the 41-dim group are identical to the reference's.  The last dim is a group of ONE dim
+    # searched with 2^14 candidates per step: TFP's log_prob (-u^2/2 - log sigma - log sqrt(2 pi), float32, ~6e-8 apart near
+    # its maximum) cannot tell candidates within |u| < 3.4e-4 of the best apart and takes the first of them; the spec's
+    # score u^2 can, and takes the closest.  Both land within that resolution of the same point.
+    per = steps * b
+    agree = [code[i * per:(i + 1) * per] == ref[i * per:(i + 1) * per] for i in range(len(starts) - 1)]
+    assert agree[:2] == [True, True] and np.diff(starts)[2] == 1
+    cut = starts[2]
+    assert np.allclose(s[:cut], gold[name + "_sample"][:cut], rtol=1e-5, atol=1e-6)
+    assert abs(float(s[cut]) - float(gold[name + "_sample"][cut])) <= 2e-3 * float(q_scale[cut])
+    dref = oracle.decode_grouped_greedy_sample(None, ref, starts[:-1], oracle.Normal(p_loc, p_scale), b, steps, seed)
+    assert np.allclose(dref, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)      # the oracle decodes the reference's stream
 
 
 @pytest.mark.parametrize("name", ["pg0", "pg1", "pg2"])

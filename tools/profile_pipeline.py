@@ -24,7 +24,7 @@ off = np.cumsum([0] + [a[0].size for a, _ in segs])
 targets = [Normal(host[0][off[i]:off[i + 1]], host[1][off[i]:off[i + 1]]) for i in range(len(segs))]
 proposals = [Normal(host[2][off[i]:off[i + 1]], host[3][off[i]:off[i + 1]]) for i in range(len(segs))]
 mgs = [mg for _, mg in segs]
-shard = D.make_is_shard() if world > 1 else None
+shard = D.make_is_shard(results=os.environ.get("CWQ_RESULTS", "own"), slice_uploads=os.environ.get("CWQ_SLICE", "1") == "1") if world > 1 else None
 specs = CIS._batch_specs(targets, proposals, 42, 20, mgs, 16)
 
 

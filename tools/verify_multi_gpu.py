@@ -35,7 +35,17 @@ def digest(res):
     return h.hexdigest()
 
 
-sharded = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard())
+def own_matches(res, ref):
+    """results="own": every call is returned by exactly one rank, and what it returns is the single-GPU result"""
+    mine = [i for i, r in enumerate(res) if r is not None]
+    ok = all(digest([res[i]]) == digest([ref[i]]) for i in mine)
+    owners = torch.zeros(len(res), dtype=torch.int32, device="cuda")
+    owners[mine] = 1
+    dist.all_reduce(owners)
+    return ok and bool((owners == 1).all().item())
+
+
+sharded = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard(results="all"))
 single = cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12)
 ok_is = digest(sharded) == digest(single)
 # the chunked pipeline (coded_importance_sampler._encode_batch_pipelined), sharded, at 2 and 3 chunks
@@ -43,7 +53,11 @@ from compression_without_quantization_b200 import coded_importance_sampler as CI
 CIS.PIPELINE_MIN_DIMS = 0
 for n_chunks in (2, 3):
     CIS.PIPELINE_CHUNKS = n_chunks
-    ok_is = ok_is and digest(cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard())) == digest(single)
+    ok_is = ok_is and digest(cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard(results="all"))) == digest(single)
+    # every rank uploads 1/world of the inputs and returns its own calls (the default of the sharded batch API)
+    ok_is = ok_is and own_matches(cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12, shard=D.make_is_shard()), single)
+    ok_is = ok_is and own_matches(cwq.code_grouped_importance_sample_batch(t, p, 42, 16, mg, 12,
+                                                                            shard=D.make_is_shard(slice_uploads=False)), single)
 CIS.PIPELINE_MIN_DIMS = 1 << 62
 gs = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6, shard=D.make_greedy_shard())
 g1 = cwq.code_grouped_greedy_sample_batch(t[2:], p[2:], 3, 8, [7, 8], 6)
