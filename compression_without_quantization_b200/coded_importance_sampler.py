@@ -95,10 +95,13 @@ def _batch_specs(targets, proposals, seeds, n_bits_per_group, max_group_size_bit
         return list(v) if isinstance(v, (list, tuple)) else [v] * ns
 
     seeds, nb, mg, dl = per(seeds), per(n_bits_per_group), per(max_group_size_bits), per(dim_kl_bit_limit)
+    f32 = (np.float32, torch.float32)
     for t, p in zip(targets, proposals):
-        _check_dtype(t, "Target")
-        _check_dtype(p, "Proposal")
-    sizes = [int(np.prod(np.shape(p.loc))) if not hasattr(p.loc, "numel") else int(p.loc.numel()) for p in proposals]
+        if getattr(t, "dtype", None) not in f32:      # the common dtypes without the general test
+            _check_dtype(t, "Target")
+        if getattr(p, "dtype", None) not in f32:
+            _check_dtype(p, "Proposal")
+    sizes = [int(p.loc.numel()) if hasattr(p.loc, "numel") else int(np.size(p.loc)) for p in proposals]
     return [E.SegmentSpec(sizes[i], seeds[i], nb[i], mg[i], dl[i], True) for i in range(ns)]
 
 
@@ -197,13 +200,27 @@ PIPELINE_MIN_DIMS = 1 << 21
 PIPELINE_CHUNKS = 4
 
 
-def _plan_chunks(sizes, n_chunks):
-    """Consecutive runs of calls: list of (first, last + 1).  The first and the last chunk get a third of the
-    dims of the inner ones: the upload of the first and the download + formatting of the last are the only
-    stages nothing overlaps."""
+def _chunk_weights(world):
+    """Relative sizes of the chunks of a pipelined batch.  One GPU: 1:3:3:1 -- the upload of the first chunk and the
+    download + formatting of the last are the only stages nothing overlaps, so both are small.  Sharded runs move 1/world
+    of the bytes per rank while every extra chunk still costs its fixed stages, so fewer chunks win (measured on 2 and
+    8 GPUs, tools/profile_pipeline.py): 1:6:1 on 2-3 ranks, 1:3 from 4 ranks on."""
+    if world <= 1:
+        return [1.0] + [3.0] * (PIPELINE_CHUNKS - 2) + [1.0] if PIPELINE_CHUNKS > 2 else [1.0] * max(PIPELINE_CHUNKS, 1)
+    if PIPELINE_CHUNKS != 4:                       # an explicit setting (tests, tools) applies to every world size
+        return [1.0] + [3.0] * (PIPELINE_CHUNKS - 2) + [1.0] if PIPELINE_CHUNKS > 2 else [1.0] * max(PIPELINE_CHUNKS, 1)
+    return [1.0, 6.0, 1.0] if world < 4 else [1.0, 3.0]
+
+
+def _plan_chunks(sizes, n_chunks, weights=None):
+    """Consecutive runs of calls: list of (first, last + 1), cut where the running dim count passes the chunk weights'
+    cumulative shares (default: a third of the inner chunks' dims for the first and the last chunk)."""
+    if weights is not None:
+        n_chunks = len(weights)
     if n_chunks <= 1 or len(sizes) <= 1:
         return [(0, len(sizes))]
-    weights = [1.0] + [3.0] * (n_chunks - 2) + [1.0] if n_chunks > 2 else [1.0, 1.0]
+    if weights is None:
+        weights = [1.0] + [3.0] * (n_chunks - 2) + [1.0] if n_chunks > 2 else [1.0, 1.0]
     total, wsum = float(sum(sizes)), float(sum(weights))
     targets = np.cumsum(weights)[:-1] * total / wsum
     bounds, acc, start = [], 0, 0
@@ -315,7 +332,9 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
     # size the all-gather of a sharded run and the expanded code) from a side-stream copy made right after G(i), i.e.
     # while chunk i-1 is still being scored, so the GPU never waits for it; download + formatting of chunk i overlap the
     # scoring of chunk i+1 and need no kernel (a kernel would queue behind the resident scoring CTAs).
+    mark("upload 0 queued")
     group(0)
+    mark("group 0 queued")
     score(0)
     mark("chunk 0 queued")
     for i in range(1, n):
@@ -347,7 +366,8 @@ def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_gr
         specs = _batch_specs(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit)
         sizes = [sp.n for sp in specs]
         if PIPELINE_MIN_DIMS <= sum(sizes) <= E.ASYNC_MAX_DIMS and min(sizes) > 0:
-            chunks = _plan_chunks(sizes, PIPELINE_CHUNKS)
+            world = shard._world_rank()[0] if shard is not None else 1
+            chunks = _plan_chunks(sizes, PIPELINE_CHUNKS, _chunk_weights(world))
             if len(chunks) > 1:
                 return _encode_batch_pipelined(list(targets), list(proposals), specs, chunks, return_indices, shard)
     job = _encode_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, "full",

@@ -19,6 +19,7 @@
 #include "cwq_common.cuh"
 #include "cwq_spec.cuh"
 #include "cwq_front.cuh"
+#include <cstdlib>
 
 namespace cwq {
 
@@ -635,7 +636,14 @@ namespace cwq {
 bool front_plan(long long n, long long max_group_size, FrontPlan* p) {
   if (n <= 0 || max_group_size < 0 || max_group_size > 128) return false;
   const int E = (int)max_group_size + 1;
-  for (int T = 1024; T <= 16384; T <<= 1) {
+  // 1024-dim tiles keep the per-tile chain walk short (latency of small inputs); above 2M dims the single-CTA chain
+  // kernel and the per-tile fixed costs weigh more and 2048 is faster (measured: profiles/r02_front_tile_size.log)
+  int t_min = n > (2LL << 20) ? 2048 : 1024;
+  if (const char* e = getenv("CWQ_FRONT_TILE")) {      // tuning knob: smallest tile size tried
+    const int v = atoi(e);
+    if (v == 2048 || v == 4096 || v == 8192 || v == 16384) t_min = v;
+  }
+  for (int T = t_min; T <= 16384; T <<= 1) {
     const long long nt = (n + T - 1) / T;
     const long long nb = (nt + CHAIN_BLOCK - 1) / CHAIN_BLOCK;
     const size_t smem_chain = (size_t)nt * E + (size_t)nb * E + (size_t)nb + (size_t)nt + 64;

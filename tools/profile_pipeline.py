@@ -34,7 +34,11 @@ def barrier():
     torch.cuda.synchronize()
 
 
-for layout in (sys.argv[1:] or ["4"]):
+for arg in (sys.argv[1:] or ["4"]):
+    # "F/4" = full uploads on every rank, "A/4" = every rank returns all results, "4" / "1:6:1" = the sharded defaults
+    flags, layout = arg.split("/") if "/" in arg else ("", arg)
+    if world > 1:
+        shard = D.make_is_shard(results="all" if "A" in flags else "own", slice_uploads="F" not in flags)
     weights = [float(x) for x in layout.split(":")] if ":" in layout else None
     if weights is None:
         chunks = CIS._plan_chunks([sp.n for sp in specs], int(layout))
@@ -54,9 +58,14 @@ for layout in (sys.argv[1:] or ["4"]):
         CIS._encode_batch_pipelined(targets, proposals, specs, chunks, False, shard, trace)
         barrier()
         times.append(time.perf_counter() - t0)
+    if world > 1:      # the slowest rank's own timeline matters: gather every rank's last mark
+        lasts = [None] * world
+        dist.all_gather_object(lasts, [(n_, round(1e3 * t_, 2)) for n_, t_ in trace])
     if rank == 0:
+        if world > 1:
+            print("   per-rank (first mark .. last mark): " + " | ".join("%.2f..%.2f" % (l[0][1], l[-1][1]) for l in lasts))
         print("layout %s chunks %s world %d: e2e median %.2f ms (min %.2f) over %d reps" % (
-            layout, chunks, world, 1e3 * float(np.median(times[2:])), 1e3 * min(times[2:]), len(times) - 2), flush=True)
+            arg, chunks, world, 1e3 * float(np.median(times[2:])), 1e3 * min(times[2:]), len(times) - 2), flush=True)
         for name, t in trace:
             print("   %-24s %8.2f ms" % (name, 1e3 * t))
 if world > 1:
