@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CWQ_LIB") or os.path.join(_HERE, "libcwq.so")   # CWQ_LIB: A/B builds of the same ABI (tools/variants)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CwqError(RuntimeError):
@@ -87,7 +87,7 @@ SIGNATURES = {
     "cwq_elias_delta_parse_host": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "cwq_ac_encode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _P, _I64, _P]),
     "cwq_ac_decode_host": (ctypes.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
-    "cwq_draw_candidates": (ctypes.c_int, [_U32, _U32, _U32, _U32, _P, _P]),
+    "cwq_draw_candidates": (ctypes.c_int, [_U32, _U32, _U32, _U32, _I32, _P, _P]),
     "cwq_stream_words": (ctypes.c_int, [_U32, _U32, _U32, _U32, _P, _P]),
     "cwq_philox4x32_10": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
 }

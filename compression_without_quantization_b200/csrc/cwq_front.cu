@@ -75,13 +75,16 @@ __device__ __forceinline__ SegLocal seg_local(const cwq_segment& sg, long long t
 // the reference's loop body from state (size, acc) at local dim j0 until the next boundary (cwq_group.cu:walk restated on
 // the tile's shared copy of kl, 32-bit indices, float32 threshold)
 __device__ __forceinline__ int walk_tile(const float* __restrict__ kl_s, int j0, int size, float acc, const SegLocal& sg) {
-  for (int j = j0; j < sg.end; ++j) {
-    const float cand = __fadd_rn(acc, kl_s[j]);
-    if (size >= sg.limit || cand >= sg.thr || j == sg.end - 1) return j;
-    acc = cand;
-    ++size;
+  if (j0 >= sg.end) return sg.end;
+  // the size test fires at j0 + (limit - size), the end-of-segment test at end - 1: whichever comes first closes the walk;
+  // before it only the budget test can
+  const int room = sg.limit > size ? sg.limit - size : 0;
+  const int jstop = j0 + room < sg.end - 1 ? j0 + room : sg.end - 1;
+  for (int j = j0; j < jstop; ++j) {
+    acc = __fadd_rn(acc, kl_s[j]);
+    if (acc >= sg.thr) return j;
   }
-  return sg.end;
+  return jstop;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -362,9 +362,10 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
   float* best = reinterpret_cast<float*>(smem_raw + (size_t)Gp * sizeof(float2) + (size_t)nq * sizeof(uint4));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t group_seed = gseed[g];
+  const float step_scale = __fmul_rn(shard_scale, NORMAL_SCALE);   // the step's N(0,1) draw is NORMAL_SCALE * y: folded into the scale
   for (int d = tid; d < Gp; d += GREEDY_THREADS) {
     best[d] = 0.0f;
-    ce[d] = make_float2(d < G ? __fmul_rn(shard_scale, tparam[s + d].y) : 0.0f, 0.0f);
+    ce[d] = make_float2(d < G ? __fmul_rn(step_scale, tparam[s + d].y) : 0.0f, 0.0f);
   }
   __syncthreads();
   for (int step = 0; step < n_steps; ++step) {
@@ -409,10 +410,10 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_encode(const float2* 
     __syncthreads();
     const uint32_t choice = s_choice;
     for (int q = tid; q < nq; q += GREEDY_THREADS) {
-      float z[4];
-      normal_quad(sseed, choice, (uint32_t)q, z);
+      float y[4];
+      raw_quad(sseed, choice, (uint32_t)q, y);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) best[4 * q + j] = __fmaf_rn(shard_scale, z[j], best[4 * q + j]);
+      for (int j = 0; j < 4; ++j) best[4 * q + j] = __fmaf_rn(step_scale, y[j], best[4 * q + j]);
     }
     __syncthreads();
   }
@@ -444,12 +445,13 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
   const long long d_begin = starts[g0], d_end = starts[g0 + ng];
   const unsigned int chunks = (n_samples + GREEDY_CHUNK - 1) / GREEDY_CHUNK;
   const unsigned long long n_units = (unsigned long long)ng * chunks;
+  const float step_scale = __fmul_rn(shard_scale, NORMAL_SCALE);
 
   for (long long i = d_begin + (long long)blockIdx.x * blockDim.x + tid; i < d_end; i += (long long)gridDim.x * blockDim.x) {
     float2 t = tparam[i];
     const float b = __fadd_rn(0.0f, shard_loc ? shard_loc[i] : 0.0f);   // best holds "running sample + this step's shard loc"
     best[i] = b;
-    ce[i] = make_float2(__fmul_rn(shard_scale, t.y), __fmul_rn(__fsub_rn(b, t.x), t.y));
+    ce[i] = make_float2(__fmul_rn(step_scale, t.y), __fmul_rn(__fsub_rn(b, t.x), t.y));
   }
   for (long long j = (long long)blockIdx.x * blockDim.x + tid; j < ng; j += (long long)gridDim.x * blockDim.x) keys[j] = 0ull;
   grid.sync();
@@ -512,12 +514,12 @@ __global__ void __launch_bounds__(GREEDY_THREADS) k_greedy_lockstep(const float2
       const uint32_t sseed = 1000u * gseed[g] + (uint32_t)step;
       for (int q = tid; q < nq; q += GREEDY_THREADS) {
         float z[4];
-        normal_quad(sseed, choice, (uint32_t)q, z);
+        raw_quad(sseed, choice, (uint32_t)q, z);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int d = 4 * q + jj;
           if (d < G) {
-            const float chosen = __fmaf_rn(shard_scale, z[jj], best[s + d]);
+            const float chosen = __fmaf_rn(step_scale, z[jj], best[s + d]);
             const float2 t = tparam[s + d];
             if (step + 1 == n_steps) { best[s + d] = chosen; continue; }
             const float b = __fadd_rn(chosen, shard_loc ? shard_loc[s + d] : 0.0f);
@@ -545,12 +547,13 @@ __global__ void __launch_bounds__(256) k_greedy_decode(const long long* __restri
   uint32_t d = (uint32_t)(i - starts[g]);
   uint32_t group_seed = gseed[g];
   const float l = shard_loc ? shard_loc[i] : 0.0f;
+  const float step_scale = __fmul_rn(shard_scale, NORMAL_SCALE);
   float b = 0.0f;
   for (int step = 0; step < n_steps; ++step) {
     float z[4];
-    normal_quad(1000u * group_seed + (uint32_t)step, indices[(long long)g * n_steps + step], d >> 2, z);
+    raw_quad(1000u * group_seed + (uint32_t)step, indices[(long long)g * n_steps + step], d >> 2, z);
     float zz = (d & 2) ? ((d & 1) ? z[3] : z[2]) : ((d & 1) ? z[1] : z[0]);
-    b = __fmaf_rn(shard_scale, zz, __fadd_rn(b, l));
+    b = __fmaf_rn(step_scale, zz, __fadd_rn(b, l));
   }
   sample[i] = __fadd_rn(__fmul_rn(p_scale[i], b), p_loc[i]);
 }
@@ -665,13 +668,13 @@ __global__ void __launch_bounds__(ASCII_THREADS) k_bits_to_ascii(const uint8_t* 
 // ------------------------------------------------------------------------------------------
 // the candidate stream, materialised (debug / oracle injection)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_draw(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_draw(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, int raw, float* __restrict__ out) {
   const uint32_t nq = (G + 3) >> 2;
   ull t = (ull)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (ull)nk * nq) return;
   uint32_t r = (uint32_t)(t / nq), q = (uint32_t)(t - (ull)r * nq);
   float z[4];
-  normal_quad(sseed, k0 + r, q, z);
+  if (raw) raw_quad(sseed, k0 + r, q, z); else normal_quad(sseed, k0 + r, q, z);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (4 * q + j < G) out[(ull)r * G + 4 * q + j] = z[j];
@@ -1204,11 +1207,11 @@ extern "C" int cwq_elias_delta_parse_host(const uint8_t* h_ascii_bits, int64_t n
   return CWQ_OK;
 }
 
-extern "C" int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, float* out, void* stream) {
+extern "C" int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, int32_t raw, float* out, void* stream) {
   if (nk == 0 || G == 0) return CWQ_OK;
   ull t = (ull)nk * ((G + 3) / 4);
   CWQ_REQUIRE(t < (1ull << 39), "too many draws for one call");
-  k_draw<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stream_seed, k0, nk, G, out);
+  k_draw<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stream_seed, k0, nk, G, raw, out);
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }

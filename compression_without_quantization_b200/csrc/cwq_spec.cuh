@@ -145,20 +145,26 @@ __device__ __forceinline__ float mantissa_to_1_2(uint32_t x) {
   return __uint_as_float(r);
 }
 
-// Two N(0,1) values from two uniform words (Box-Muller, 23-bit uniforms).
-__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ze, float& zo) {
+// The stream's RAW draws y: Box-Muller of two 23-bit uniforms WITHOUT the factor sqrt(2 ln 2):
+//   y = sqrt(-lg2 u1) * (cos t, sin t),   y ~ N(0, 1 / (2 ln 2));   the N(0,1) draw is  z = NORMAL_SCALE * y.
+// The hot loops never form z: the factor is folded into what multiplies the draw (importance sampler: a' = a * 2 ln 2,
+// b' = b * sqrt(2 ln 2); greedy: step scale s' = s * sqrt(2 ln 2)), which removes one multiply per Box-Muller pair from
+// the candidate loop.  z itself is formed only where a latent is output (decode, outliers, the seam's N(0,1) view).
+constexpr float NORMAL_SCALE = 1.1774100f;       // float32(sqrt(2 ln 2))
+constexpr float NORMAL_SCALE_SQ = 1.3862944f;    // float32(2 ln 2)
+
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& ye, float& yo) {
   float f1 = mantissa_to_1_2(xa);  // [1,2)
   float f2 = mantissa_to_1_2(xb);
   float u1 = __fsub_rn(2.0f, f1);                                // (0,1], exact
   float th = __fmaf_rn(f2, 6.2831855f, -9.424778f);              // [-pi, pi)
   float l, r, c, s;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
-  float r2 = __fmul_rn(l, -1.3862944f);                          // -2 ln u1
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));         // <= 0
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-l));        // the negation is a source modifier of MUFU.SQRT
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
-  ze = __fmul_rn(r, c);
-  zo = __fmul_rn(r, s);
+  ye = __fmul_rn(r, c);
+  yo = __fmul_rn(r, s);
 }
 
 __device__ __forceinline__ void box_muller_quad(const uint32_t (&w)[4], float (&z)[4]) {
@@ -220,10 +226,16 @@ __device__ __forceinline__ void quad_words(uint32_t sseed, uint32_t k, uint32_t 
   }
 }
 
-__device__ __forceinline__ void normal_quad(uint32_t sseed, uint32_t k, uint32_t quad, float (&z)[4]) {
+// raw draws y of one quad (what the candidate loops score), and the N(0,1) draws z = NORMAL_SCALE * y (what is output)
+__device__ __forceinline__ void raw_quad(uint32_t sseed, uint32_t k, uint32_t quad, float (&y)[4]) {
   uint32_t w[4];
   quad_words(sseed, k, quad, w);
-  box_muller_quad(w, z);
+  box_muller_quad(w, y);
+}
+__device__ __forceinline__ void normal_quad(uint32_t sseed, uint32_t k, uint32_t quad, float (&z)[4]) {
+  raw_quad(sseed, k, quad, z);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __fmul_rn(NORMAL_SCALE, z[i]);
 }
 
 // Deterministic natural log / exp (Cephes-style minimax polynomials), bit-identical to
@@ -305,7 +317,10 @@ __device__ __forceinline__ PrologueDim is_prologue_dim(float ql, float qs, float
   const float iv = __fdiv_rn(1.0f, __fmul_rn(ts, ts));
   const bool rep = (r.m & 1) != 0;
   r.kl = rep ? 0.0f : k0;
-  r.coef = rep ? make_float2(0.0f, 0.0f) : make_float2(__fmaf_rn(-0.5f, iv, 0.5f), __fmul_rn(tl, iv));
+  // log q(z) - log p(z) = a z^2 + b z + const with z = NORMAL_SCALE * y: the kernels score the raw draw y with
+  // (a * 2 ln 2, b * sqrt(2 ln 2))
+  r.coef = rep ? make_float2(0.0f, 0.0f)
+               : make_float2(__fmul_rn(__fmaf_rn(-0.5f, iv, 0.5f), NORMAL_SCALE_SQ), __fmul_rn(__fmul_rn(tl, iv), NORMAL_SCALE));
   return r;
 }
 

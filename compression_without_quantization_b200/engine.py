@@ -661,13 +661,14 @@ class GreedyJob:
 # ----------------------------------------------------------------------------------------------
 # the candidate stream (misc.py:3-17)
 # ----------------------------------------------------------------------------------------------
-def draw_candidates(stream_seed, k0, nk, G, device=None):
-    """Rows k0..k0+nk-1 of the N(0,1) table of stream `stream_seed` as a float32 [nk, G] CUDA tensor."""
+def draw_candidates(stream_seed, k0, nk, G, device=None, raw=False):
+    """Rows k0..k0+nk-1 of the candidate table of stream `stream_seed` as a float32 [nk, G] CUDA tensor: N(0,1) draws, or
+    with raw=True the stream's raw draws y (z = float32(sqrt(2 ln 2)) * y) that the candidate loops score."""
     device = device or cuda_device()
     out = torch.empty((int(nk), int(G)), dtype=torch.float32, device=device)
     if nk and G:
-        _lib.call("cwq_draw_candidates", int(stream_seed) & 0xFFFFFFFF, int(k0) & 0xFFFFFFFF, int(nk), int(G), _ptr(out),
-                  _stream())
+        _lib.call("cwq_draw_candidates", int(stream_seed) & 0xFFFFFFFF, int(k0) & 0xFFFFFFFF, int(nk), int(G), 1 if raw else 0,
+                  _ptr(out), _stream())
     return out
 
 

@@ -21,5 +21,7 @@ def stateless_normal_sample(loc, scale, num_samples, seed):
 
 
 def candidate_rows(stream_seed, k0, nk, G):
-    """float32[nk, G] numpy: rows k0.. of stream `stream_seed` -- the `normal_source` the oracle takes."""
-    return E.draw_candidates(stream_seed, k0, nk, G).cpu().numpy()
+    """float32[nk, G] numpy: rows k0.. of the RAW draws y of stream `stream_seed` -- the `normal_source` the oracle takes
+    (the injection seam of the parity harness).  The N(0,1) draw is float32(sqrt(2 ln 2)) * y; the candidate loops score y
+    itself with that factor folded into their coefficients."""
+    return E.draw_candidates(stream_seed, k0, nk, G, raw=True).cpu().numpy()

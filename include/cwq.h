@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CWQ_ABI_VERSION 2
+#define CWQ_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CWQ_API __attribute__((visibility("default")))
@@ -251,8 +251,12 @@ CWQ_API int cwq_ac_decode_host(const int64_t* h_counts, int32_t n_symbols, const
                        int64_t* h_bits_used);
 
 /* ---- the candidate stream (debug / oracle injection seam, misc.py:3-17) ---------------------- */
-/* rows k0..k0+nk-1, G columns, of the N(0,1) table of stream `stream_seed`: out[nk * G] */
-CWQ_API int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, float* out, void* stream);
+/* rows k0..k0+nk-1, G columns, of the candidate table of stream `stream_seed`: out[nk * G].  raw = 0: the N(0,1) draws z
+ * that stand in for tf.random.stateless_normal; raw = 1: the stream's raw draws y, z = float32(sqrt(2 ln 2)) * y, which are
+ * what the candidate loops score (the factor is folded into their coefficients) and what the parity harness injects into
+ * the oracle. */
+CWQ_API int cwq_draw_candidates(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t G, int32_t raw, float* out,
+                        void* stream);
 /* the raw Philox words of blocks j = 0..nq-1 of rows k0..k0+nk-1 (block(s,k,j)): out[nk * nq * 4] */
 CWQ_API int cwq_stream_words(uint32_t stream_seed, uint32_t k0, uint32_t nk, uint32_t nq, uint32_t* out, void* stream);
 /* plain Philox4x32-10 on n (counter, key) pairs: ctr[4n], key[2n], out[4n] */

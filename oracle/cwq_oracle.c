@@ -72,15 +72,18 @@ static inline void stream_block(uint32_t sseed, uint32_t k, uint32_t j, uint32_t
   cwqo_philox4x32_10(ctr, key, o);
 }
 
-static inline void box_muller(uint32_t xa, uint32_t xb, float* ze, float* zo) {
+/* The stream's RAW draws: y = sqrt(-lg2 u1) (cos t, sin t), y ~ N(0, 1 / (2 ln 2)); the N(0,1) draw is
+ * z = NORMAL_SCALE * y.  The candidate loops score y with the factor folded into the coefficients / the step scale. */
+#define NORMAL_SCALE 1.1774100f    /* float32(sqrt(2 ln 2)) */
+#define NORMAL_SCALE_SQ 1.3862944f /* float32(2 ln 2) */
+static inline void box_muller(uint32_t xa, uint32_t xb, float* ye, float* yo) {
   float f1 = u2f((xa & 0x007fffffu) | 0x3f800000u); /* [1,2) */
   float f2 = u2f((xb & 0x007fffffu) | 0x3f800000u);
   float u1 = 2.0f - f1;                              /* (0,1], exact */
   float th = fmaf(f2, 6.2831855f, -9.424778f);       /* [-pi, pi) */
-  float r2 = log2f(u1) * -1.3862944f;                /* -2 ln u1 */
-  float r = sqrtf(r2);
-  *ze = r * cosf(th);
-  *zo = r * sinf(th);
+  float r = sqrtf(-log2f(u1));
+  *ye = r * cosf(th);
+  *yo = r * sinf(th);
 }
 
 static inline uint32_t harvest(uint32_t w0, uint32_t w1, uint32_t w2) {
@@ -98,17 +101,17 @@ static inline void quad_words(uint32_t sseed, uint32_t k, uint32_t quad, uint32_
   for (int i = 0; i < 4; ++i) w[i] = harvest(o0[i], o1[i], o2[i]);
 }
 
-static inline void normal_quad(uint32_t sseed, uint32_t k, uint32_t quad, float z[4]) {
+static inline void raw_quad(uint32_t sseed, uint32_t k, uint32_t quad, float z[4]) {
   uint32_t w[4];
   quad_words(sseed, k, quad, w);
   box_muller(w[0], w[1], &z[0], &z[1]);
   box_muller(w[2], w[3], &z[2], &z[3]);
 }
 
-/* Same values as normal_quad for callers that walk the quads of ONE row in order (0, 1, 2, ...): the three
+/* Same values as raw_quad for callers that walk the quads of ONE row in order (0, 1, 2, ...): the three
  * blocks of the current unit are kept in `unit` so that quad 3 does not recompute them (the candidate loops
  * timed as the CPU baseline do the same work per candidate as the GPU kernels: 3 blocks per 16 dims). */
-static inline void normal_quad_seq(uint32_t sseed, uint32_t k, uint32_t quad, uint32_t unit[3][4], float z[4]) {
+static inline void raw_quad_seq(uint32_t sseed, uint32_t k, uint32_t quad, uint32_t unit[3][4], float z[4]) {
   uint32_t qi = quad & 3u, w[4];
   if (qi < 3u) {
     stream_block(sseed, k, 3u * (quad >> 2) + qi, unit[qi]);
@@ -120,14 +123,15 @@ static inline void normal_quad_seq(uint32_t sseed, uint32_t k, uint32_t quad, ui
   box_muller(w[2], w[3], &z[2], &z[3]);
 }
 
-/* rows k0..k0+nk-1, columns 0..G-1, row-major [nk, G]  (misc.py:10-15 with loc=0, scale=1) */
-void cwqo_normals(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, float* out) {
+/* rows k0..k0+nk-1, columns 0..G-1, row-major [nk, G]: raw != 0 -> the raw draws y (what the candidate loops score and
+ * the injection seam carries), raw == 0 -> N(0,1) draws z = NORMAL_SCALE * y (misc.py:10-15 with loc=0, scale=1) */
+void cwqo_normals(uint32_t sseed, uint32_t k0, uint32_t nk, uint32_t G, int raw, float* out) {
   for (uint32_t i = 0; i < nk; ++i) {
     uint32_t unit[3][4];
     for (uint32_t q = 0; q * 4 < G; ++q) {
       float z[4];
-      normal_quad_seq(sseed, k0 + i, q, unit, z);
-      for (uint32_t j = 0; j < 4 && q * 4 + j < G; ++j) out[(size_t)i * G + q * 4 + j] = z[j];
+      raw_quad_seq(sseed, k0 + i, q, unit, z);
+      for (uint32_t j = 0; j < 4 && q * 4 + j < G; ++j) out[(size_t)i * G + q * 4 + j] = raw ? z[j] : NORMAL_SCALE * z[j];
     }
   }
 }
@@ -279,8 +283,9 @@ void cwqo_group_totals(const float* kl, const int64_t* starts, int64_t n_groups,
 void cwqo_is_coef(const float* t_loc, const float* t_scale, int64_t n, float* a, float* b) {
   for (int64_t i = 0; i < n; ++i) {
     float iv = 1.0f / (t_scale[i] * t_scale[i]);
-    a[i] = fmaf(-0.5f, iv, 0.5f);
-    b[i] = t_loc[i] * iv;
+    /* log q(z) - log p(z) = a z^2 + b z + const, z = NORMAL_SCALE * y: coefficients of the raw draw y */
+    a[i] = fmaf(-0.5f, iv, 0.5f) * NORMAL_SCALE_SQ;
+    b[i] = (t_loc[i] * iv) * NORMAL_SCALE;
   }
 }
 
@@ -296,7 +301,7 @@ uint32_t cwqo_is_encode_group(const float* a, const float* b, int32_t G, uint32_
     for (int32_t q = 0; q < nq; ++q) {
       float z[4];
       if (inj) { for (int j = 0; j < 4; ++j) z[j] = (q * 4 + j < G) ? inj[(size_t)k * G + q * 4 + j] : 0.0f; }
-      else normal_quad_seq(sseed, k, (uint32_t)q, unit, z);
+      else raw_quad_seq(sseed, k, (uint32_t)q, unit, z);
       for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
         int d = q * 4 + j;
         float w = fmaf(a[d], z[j], b[d]);
@@ -312,7 +317,7 @@ uint32_t cwqo_is_encode_group(const float* a, const float* b, int32_t G, uint32_
 
 /* CIS:104-109 with a counter-based stream: row `index` only */
 void cwqo_is_decode_group(int32_t G, uint32_t index, uint32_t sseed, float* out) {
-  cwqo_normals(sseed, index, 1, (uint32_t)G, out);
+  cwqo_normals(sseed, index, 1, (uint32_t)G, 0, out);
 }
 
 /* ---- a tiny pthread parallel-for over groups (bench.py cpu_baseline / --impl reference) ---- */
@@ -360,6 +365,9 @@ void cwqo_is_encode_groups(const float* a, const float* b, const int64_t* starts
 float cwqo_greedy_shard_scale(float rho, int32_t n_steps) {
   return rho / (float)sqrt((double)n_steps);
 }
+/* what multiplies a RAW draw in one greedy step */
+float cwqo_greedy_step_scale(float shard_scale) { return shard_scale * NORMAL_SCALE; }
+float cwqo_normal_scale(void) { return NORMAL_SCALE; }
 
 static inline uint32_t greedy_stream_seed(uint32_t group_seed, uint32_t step) {
   return 1000u * group_seed + step; /* CGS:55  seed = 1000 * seed + i, wrapping u32 */
@@ -373,7 +381,8 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, const fl
   float* isig = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1));
   float* c = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1));
   float* e = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1));
-  for (int32_t d = 0; d < G; ++d) { isig[d] = 1.0f / t_scale[d]; c[d] = shard_scale * isig[d]; best_out[d] = 0.0f; }
+  const float step_scale = shard_scale * NORMAL_SCALE;   /* the step's N(0,1) draw is NORMAL_SCALE * y */
+  for (int32_t d = 0; d < G; ++d) { isig[d] = 1.0f / t_scale[d]; c[d] = step_scale * isig[d]; best_out[d] = 0.0f; }
   int32_t nq = (G + 3) / 4;
   for (int32_t step = 0; step < n_steps; ++step) {
     uint32_t ss = greedy_stream_seed(group_seed, (uint32_t)step);
@@ -389,7 +398,7 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, const fl
       for (int32_t q = 0; q < nq; ++q) {
         float z[4];
         if (inj) { for (int j = 0; j < 4; ++j) z[j] = (q * 4 + j < G) ? inj[((size_t)step * n_samples + k) * G + q * 4 + j] : 0.0f; }
-        else normal_quad_seq(ss, k, (uint32_t)q, unit, z);
+        else raw_quad_seq(ss, k, (uint32_t)q, unit, z);
         for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
           int d = q * 4 + j;
           float u = fmaf(z[j], c[d], e[d]);
@@ -403,8 +412,8 @@ void cwqo_greedy_encode_group(const float* t_loc, const float* t_scale, const fl
     for (int32_t q = 0; q < nq; ++q) {
       float z[4];
       if (inj) { for (int j = 0; j < 4; ++j) z[j] = (q * 4 + j < G) ? inj[((size_t)step * n_samples + best_k) * G + q * 4 + j] : 0.0f; }
-      else normal_quad(ss, best_k, (uint32_t)q, z);
-      for (int j = 0; j < 4 && q * 4 + j < G; ++j) best_out[q * 4 + j] = fmaf(shard_scale, z[j], best_out[q * 4 + j]);
+      else raw_quad(ss, best_k, (uint32_t)q, z);
+      for (int j = 0; j < 4 && q * 4 + j < G; ++j) best_out[q * 4 + j] = fmaf(step_scale, z[j], best_out[q * 4 + j]);
     }
   }
   free(isig); free(c); free(e);
@@ -415,14 +424,15 @@ void cwqo_greedy_decode_group(int32_t G, int32_t n_steps, float shard_scale, con
                               const uint32_t* indices, float* out) {
   for (int32_t d = 0; d < G; ++d) out[d] = 0.0f;
   int32_t nq = (G + 3) / 4;
+  const float step_scale = shard_scale * NORMAL_SCALE;
   for (int32_t step = 0; step < n_steps; ++step) {
     uint32_t ss = greedy_stream_seed(group_seed, (uint32_t)step);
     for (int32_t q = 0; q < nq; ++q) {
       float z[4];
-      normal_quad(ss, indices[step], (uint32_t)q, z);
+      raw_quad(ss, indices[step], (uint32_t)q, z);
       for (int j = 0; j < 4 && q * 4 + j < G; ++j) {
         int d = q * 4 + j;
-        out[d] = fmaf(shard_scale, z[j], out[d] + (shard_loc ? shard_loc[d] : 0.0f));
+        out[d] = fmaf(step_scale, z[j], out[d] + (shard_loc ? shard_loc[d] : 0.0f));
       }
     }
   }
@@ -473,7 +483,7 @@ float cwqo_dequantize_u16(uint16_t q) { return fmaf((float)q, 60.0f / 65535.0f, 
  * z = lane 0 of block(k = dim, q = 0) of stream (seed + 0x9E3779B9), value = q_scale * z + q_loc. */
 float cwqo_outlier_normal(uint32_t seed, uint32_t dim) {
   float z[4];
-  normal_quad(seed + 0x9E3779B9u, dim, 0u, z);
-  return z[0];
+  raw_quad(seed + 0x9E3779B9u, dim, 0u, z);
+  return NORMAL_SCALE * z[0];
 }
 

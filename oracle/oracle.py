@@ -73,6 +73,9 @@ def lib():
                                            _c_f32p, _c_f32p]
         L.cwqo_greedy_shard_scale.restype = ctypes.c_float
         L.cwqo_greedy_shard_scale.argtypes = [ctypes.c_float, ctypes.c_int32]
+        L.cwqo_greedy_step_scale.restype = ctypes.c_float
+        L.cwqo_greedy_step_scale.argtypes = [ctypes.c_float]
+        L.cwqo_normal_scale.restype = ctypes.c_float
         L.cwqo_quantize_u16.restype = ctypes.c_uint16
         L.cwqo_quantize_u16.argtypes = [ctypes.c_float]
         L.cwqo_dequantize_u16.restype = ctypes.c_float
@@ -130,21 +133,39 @@ def quad_words(stream_seed, k0, nk, nq):
     return out
 
 
-def default_normal_source(stream_seed, k0, nk, G):
-    """misc.py:10-11 restated on the spec stream: rows k0..k0+nk-1 of the [K, G] N(0,1) table."""
+NORMAL_SCALE = np.float32(1.1774100)     # float32(sqrt(2 ln 2)): the N(0,1) draw is NORMAL_SCALE * (raw draw), DESIGN.md 3.1
+
+
+def _rows(stream_seed, k0, nk, G, raw):
     out = np.zeros((nk, G), dtype=np.float32)
     if nk > 0 and G > 0:
         lib().cwqo_normals(ctypes.c_uint32(_u32(stream_seed)), ctypes.c_uint32(_u32(k0)), ctypes.c_uint32(nk),
-                           ctypes.c_uint32(G), _p(out, _c_f32p))
+                           ctypes.c_uint32(G), ctypes.c_int(raw), _p(out, _c_f32p))
     return out
+
+
+def default_normal_source(stream_seed, k0, nk, G):
+    """The injection seam: rows k0..k0+nk-1 of the [K, G] table of RAW draws y of the spec stream (y ~ N(0, 1/(2 ln 2));
+    the candidate loops score y directly).  A `normal_source` passed to the functions below must return raw draws too --
+    the engine's are compression_without_quantization_b200.misc.candidate_rows."""
+    return _rows(stream_seed, k0, nk, G, 1)
+
+
+def normal_rows(stream_seed, k0, nk, G):
+    """misc.py:10-11 restated on the spec stream: rows of the [K, G] N(0,1) table, z = NORMAL_SCALE * y."""
+    return _rows(stream_seed, k0, nk, G, 0)
+
+
+def as_standard_normal(normal_source):
+    """N(0,1) view of a raw-draw source: what stands in for tf.random.stateless_normal in the reference harness."""
+    return lambda seed, k0, nk, G: (NORMAL_SCALE * np.asarray(normal_source(seed, k0, nk, G), dtype=np.float32)).astype(np.float32)
 
 
 def stateless_normal_sample(loc, scale, num_samples, seed, normal_source=None):
     """misc.py:3-17: [num_samples, *loc.shape] normals, then scale * z + loc."""
-    src = normal_source or default_normal_source
     loc = np.asarray(loc, dtype=np.float32)
     scale = np.asarray(scale, dtype=np.float32)
-    z = src(seed, 0, int(num_samples), int(loc.size)).reshape((int(num_samples),) + loc.shape)
+    z = _normal(normal_source, seed, 0, int(num_samples), int(loc.size)).reshape((int(num_samples),) + loc.shape)
     return (scale[None] * z + loc[None]).astype(np.float32)
 
 
@@ -370,8 +391,14 @@ def _check_f32(dist, what):
 
 
 def _draw(normal_source, stream_seed, k0, nk, G):
+    """raw draws y (what the encode loops are fed)"""
     src = normal_source or default_normal_source
     return np.ascontiguousarray(src(_u32(stream_seed), k0, nk, G), dtype=np.float32).reshape(nk, G)
+
+
+def _normal(normal_source, stream_seed, k0, nk, G):
+    """N(0,1) draws z = NORMAL_SCALE * y (what a latent is made of), one float32 multiply"""
+    return (NORMAL_SCALE * _draw(normal_source, stream_seed, k0, nk, G)).astype(np.float32)
 
 
 def code_importance_sample(t_loc, t_scale, p_loc, p_scale, n_coding_bits, seed, return_index_only=False,
@@ -386,7 +413,7 @@ def code_importance_sample(t_loc, t_scale, p_loc, p_scale, n_coding_bits, seed, 
     a, b = is_coef(r_loc, r_scale)
     draws = _draw(normal_source, seed, 0, K, G) if normal_source is not None else None
     index, _ = is_encode_group(a, b, K, seed, draws)
-    z = _draw(normal_source, seed, index, 1, G)
+    z = _normal(normal_source, seed, index, 1, G)
     best_sample = (p_scale[None] * z + p_loc[None]).astype(np.float32)
     if return_index_only:
         return best_sample, index + 1
@@ -399,11 +426,11 @@ def decode_importance_sample(sample_index, p_loc, p_scale, seed, use_index=False
     G = p_loc.size
     if use_index:
         index = int(sample_index) - 1
-        z = _draw(normal_source, seed, index, 1, G)
+        z = _normal(normal_source, seed, index, 1, G)
         return (p_scale[None] * z + p_loc[None]).astype(np.float32)
     num, code_length = elias_delta_decode(sample_index)
     index = num - 1
-    z = _draw(normal_source, seed, index, 1, G)
+    z = _normal(normal_source, seed, index, 1, G)
     return (p_scale[None] * z + p_loc[None]).astype(np.float32), code_length, index
 
 
@@ -421,7 +448,7 @@ def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_grou
     t_loc, t_scale, kl_divs, mask = is_prologue(q_loc, q_scale, p_loc, p_scale, dim_kl_bit_limit)
     outlier_indices = np.nonzero(mask & 2)[0].astype(np.int64)
     # CIS:150 target.sample(), seeded by the spec (the reference's draw is unseeded)
-    z_out = np.array([_draw(normal_source, _u32(seed) + OUTLIER_STREAM_OFFSET, int(i) & 0xFFFFFFFF, 1, 1)[0, 0]
+    z_out = np.array([_normal(normal_source, _u32(seed) + OUTLIER_STREAM_OFFSET, int(i) & 0xFFFFFFFF, 1, 1)[0, 0]
                       for i in outlier_indices], dtype=np.float32)
     target_samples_at_outliers = (q_scale[outlier_indices] * z_out + q_loc[outlier_indices]).astype(np.float32)
     outlier_samples = quantize_u16(target_samples_at_outliers)
@@ -446,7 +473,7 @@ def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_grou
         index, _ = is_encode_group(a[s:e], b[s:e], int(K[i]), ss, draws)
         indices.append(index + 1)
         if G > 0:
-            sample[s:e] = _draw(normal_source, ss, index, 1, G)[0]
+            sample[s:e] = _normal(normal_source, ss, index, 1, G)[0]
     if return_indices_only:
         return tuple(indices)
     # CIS:262-267
@@ -484,7 +511,7 @@ def decode_grouped_importance_sample(sess, bitcode, group_start_indices, proposa
             pos += codelength
             index = num - 1
         if e > s:
-            sample[s:e] = _draw(normal_source, _u32(seed + i), index, 1, e - s)[0]
+            sample[s:e] = _normal(normal_source, _u32(seed + i), index, 1, e - s)[0]
     sample = (p_scale * sample + p_loc).astype(np.float32)
     # CIS:351-361
     outlier_indices = np.asarray(outlier_indices, dtype=np.int64).reshape(-1)
@@ -518,12 +545,13 @@ def code_greedy_sample(t_loc, t_scale, p_loc, p_scale, n_bits_per_step, n_steps,
 
 def _greedy_replay(G, indices, n_steps, shard_scale, group_seed, normal_source, shard_loc=None):
     out = np.zeros(G, np.float32)
+    step_scale = float(lib().cwqo_greedy_step_scale(ctypes.c_float(shard_scale)))      # shard_scale * NORMAL_SCALE: the rows are raw
     for i in range(n_steps):
         z = np.ascontiguousarray(_draw(normal_source, 1000 * _u32(group_seed) + i, int(indices[i]), 1, G)[0])
         if shard_loc is not None:
             out = (out + shard_loc).astype(np.float32)
         if G > 0:
-            lib().cwqo_axpy_fma(ctypes.c_float(shard_scale), _p(z, _c_f32p), _p(out, _c_f32p), ctypes.c_int64(G))
+            lib().cwqo_axpy_fma(ctypes.c_float(step_scale), _p(z, _c_f32p), _p(out, _c_f32p), ctypes.c_int64(G))
     return out
 
 

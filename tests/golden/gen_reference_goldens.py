@@ -27,7 +27,7 @@ from oracle import oracle as O  # noqa: E402
 from oracle import tf_shim  # noqa: E402
 
 tf = tf_shim.install()
-tf_shim.set_normal_source(O.default_normal_source)
+tf_shim.set_normal_source(O.as_standard_normal(O.default_normal_source))   # tf.random.stateless_normal: N(0,1) = sqrt(2 ln 2) * raw
 sys.path.insert(0, "/root/reference/code")
 import tqdm as _tqdm  # noqa: E402
 

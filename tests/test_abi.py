@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.cwq_abi_version() == 2
+    assert lib.cwq_abi_version() == 3
 
 
 def test_ctypes_table_mirrors_the_header():

@@ -42,7 +42,7 @@ def test_stream_units_three_blocks_plus_harvested_quad(oracle):
         top = blocks[:, 3 * u:3 * u + 3] >> 24
         assert np.array_equal(quads[:, 4 * u + 3], top[:, 0] | (top[:, 1] << 8) | (top[:, 2] << 16))
     # the normals are Box-Muller of the low 23 bits of those words (float64 here, libm float32 in the oracle)
-    z = oracle.default_normal_source(seed, k0, nk, 44)
+    z = oracle.normal_rows(seed, k0, nk, 44)
     m = (quads & 0x7FFFFF).astype(np.float64) / 2.0 ** 23
     u1, th = 1.0 - m[..., 0::2], 2 * np.pi * m[..., 1::2] - np.pi
     r = np.sqrt(-2 * np.log(u1))
@@ -51,17 +51,17 @@ def test_stream_units_three_blocks_plus_harvested_quad(oracle):
 
 
 def test_normal_stream_statistics_and_addressing(oracle):
-    z = oracle.default_normal_source(42, 0, 40000, 16)
+    z = oracle.normal_rows(42, 0, 40000, 16)
     assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3 and abs(np.mean(z ** 4) - 3) < 0.05
     assert np.abs(z).max() < 5.7   # 23-bit uniforms: r <= sqrt(-2 ln 2^-23)
-    assert np.array_equal(oracle.default_normal_source(42, 100, 5, 7), z[100:105, :7])
-    assert not np.array_equal(oracle.default_normal_source(43, 0, 4, 16), z[:4])
+    assert np.array_equal(oracle.normal_rows(42, 100, 5, 7), z[100:105, :7])
+    assert not np.array_equal(oracle.normal_rows(43, 0, 4, 16), z[:4])
 
 
 def test_harvested_quad_is_standard_normal_and_uncorrelated_with_the_direct_quads(oracle):
     """Dims 12..15 of a unit come from the top bytes of the words whose low 23 bits give dims 0..11:
     same distribution, no linear correlation between any two dims of a unit (nor between their squares)."""
-    z = oracle.default_normal_source(7, 0, 60000, 32).astype(np.float64)
+    z = oracle.normal_rows(7, 0, 60000, 32).astype(np.float64)
     for d in range(32):
         col = z[:, d]
         assert abs(col.mean()) < 0.02 and abs(col.std() - 1) < 0.02 and abs(np.mean(col ** 4) - 3) < 0.15
@@ -80,7 +80,7 @@ def test_harvested_quad_ks_chi2_and_joint_independence(oracle):
     Fixed seeds: the p-values are constants, the thresholds only have to sit below them."""
     from scipy import stats
     n = 200000
-    z = oracle.default_normal_source(11, 0, n, 16).astype(np.float64)
+    z = oracle.normal_rows(11, 0, n, 16).astype(np.float64)
     words = oracle.quad_words(11, 0, n, 4)                       # [n, 4 quads, 4 words]
     pvals = {}
     for d in range(12, 16):
@@ -257,6 +257,42 @@ def test_per_group_greedy_with_proposal_loc_matches_unmodified_reference_run(ora
     d = oracle.decode_greedy_sample(code, p_loc, p_scale, b, steps, seed, rho=rho)
     assert np.allclose(d, gold[name + "_decoded"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(d, best)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's parity harness: the unmodified reference fed the ENGINE's own draws (saved from a B200 through the
+# injection seam, tests/golden/gen_engine_draw_goldens.py); the GPU tests compare the engine with the same files.
+# ------------------------------------------------------------------------------------------------
+def _engine_draw_source():
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_engine_draw_goldens as G
+    draws = np.load(os.path.join(GOLD, "engine_draws.npz"))
+    return G, G.Tables(stored={k: draws[k] for k in draws.files}), np.load(os.path.join(GOLD, "reference_engine_draws.npz"))
+
+
+def test_oracle_equals_reference_run_on_engine_draws(oracle):
+    G, src, gold = _engine_draw_source()
+    for name, n, key, nontrivial, seed, bits, m, limit in G.IS_CASES:
+        q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
+        s, code, starts, (oi, oq) = oracle.code_grouped_importance_sample(
+            None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), seed, bits, m, limit, normal_source=src,
+            outlier_mode="reference")
+        assert np.array_equal(starts, gold[name + "_starts"]) and code == gold[name + "_bitcode"].tobytes(), name
+        assert np.array_equal(oi, gold[name + "_oidx"]) and np.array_equal(oq, gold[name + "_oq"]), name
+        assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6), name
+    assert any(gold[c[0] + "_oidx"].size for c in G.IS_CASES)          # the outlier path is covered
+    for name, n, key, nontrivial, seed, steps, b, m in G.GR_CASES:
+        q_loc, q_scale, p_loc, p_scale = gold[name + "_in"]
+        s, code, starts = oracle.code_grouped_greedy_sample(None, oracle.Normal(q_loc, q_scale), oracle.Normal(p_loc, p_scale), steps, b,
+                                                            seed, m, normal_source=src)
+        assert starts == [int(x) for x in gold[name + "_starts"]] and code.encode() == gold[name + "_bitcode"].tobytes(), name
+        assert np.allclose(s, gold[name + "_sample"], rtol=1e-5, atol=1e-6), name
+    for name, Gd, key, seed, steps, b, rho in G.PG_CASES:
+        t_loc, t_scale, p_loc, p_scale = gold[name + "_in"]
+        best, code = oracle.code_greedy_sample(t_loc, t_scale, p_loc, p_scale, b, steps, seed, rho=rho, normal_source=src)
+        assert code.encode() == gold[name + "_bitcode"].tobytes(), name
+        assert np.allclose(best, gold[name + "_sample"], rtol=1e-5, atol=1e-6), name
 
 
 def test_oracle_round_trips_and_injection_seam(oracle):

@@ -80,12 +80,23 @@ def main():
     ms = sum(times) / len(times)
     ng = job.groups.n_groups
     cd = float(job.n) * args.n_steps * (1 << args.n_bits)
-    digest = int(job.indices.to(torch.int64).sum().item()) ^ int(job.bits.to(torch.int64).sum().item())
+    # position-weighted checksums of the index stream, the packed bitstream and the decoded latents: equal across rank counts
+    def checksum(x):
+        x = x.reshape(-1)
+        w = (torch.arange(x.numel(), device=x.device, dtype=torch.int64) % 65521) + 1
+        return int((x.to(torch.int64) * w).sum().item()) & 0xFFFFFFFFFFFF
+    digest = "{:012x}-{:012x}-{:012x}".format(checksum(job.indices), checksum(job.bits), checksum(job.sample.view(torch.int32)))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = sms * 128 * 1.965e9
     if rank == 0:
         print(json.dumps({"config": "configs[4]: {} x 3840x2160 level-1 latents, greedy {} x 2^{}".format(args.images, args.n_steps, args.n_bits),
                           "n_gpus": world, "images": args.images, "dims": job.n, "groups": ng, "ms_per_step": ms,
                           "groups_per_s": ng / ms * 1e3, "candidates_per_s": ng * args.n_steps * (1 << args.n_bits) / ms * 1e3,
                           "candidate_dims_per_s": cd / ms * 1e3, "steps": args.steps, "digest": digest,
+                          # 18.5 algorithmic thread-instructions per candidate-dim (greedy); 15.7 executed (ncu,
+                          # profiles/r01_greedy_ncu_summary.md); peak = SMs x 128 lanes x 1965 MHz per GPU
+                          "roofline_frac": cd / ms * 1e3 * 18.5 / (issue_peak * world),
+                          "roofline_frac_executed": cd / ms * 1e3 * 15.7 / (issue_peak * world),
                           "gpu_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                           "scaling": "weak when --images grows with the ranks (8 per GPU), strong for a fixed --images"}), flush=True)
     if world > 1:

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tests/golden/gen_engine_draw_goldens.py --dump 2>&1 | tail -2
+timeout 500 python -m pytest tests -m gpu -x -q -k "not identical_draws" 2>&1 | tail -8
+timeout 200 python tools/profile_small.py --batch | cut -c1-500
+timeout 200 python tools/profile_small.py | cut -c1-420
+timeout 100 python tools/gpu/dbg_latency.py 2>&1 | head -60
