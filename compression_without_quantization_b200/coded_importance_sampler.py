@@ -126,7 +126,10 @@ def _encode_batch(targets, proposals, seeds, n_bits_per_group, max_group_size_bi
         if shard is None:
             stages = {"groups": L.STAGE_GROUP, "indices": L.STAGE_GROUP | L.STAGE_SCORE,
                       "full": L.STAGE_GROUP | L.STAGE_SCORE | L.STAGE_FINISH}[stage]
-            return job.launch(stages).sync_groups()
+            job.launch(stages)
+            if stage == "full":
+                return job               # _host_views fetches the counts and the results with two synchronisations in all
+            return job.sync_groups()
         job.launch(L.STAGE_GROUP)
         if stage != "groups":
             shard(job)
@@ -168,13 +171,29 @@ def _host_views(job, with_bits, calls=None):
     one small copy for the counts, then one batch of copies for the payload.  No kernel runs on this stream unless the
     '0'/'1' expansion has not been queued yet."""
     s0, s1 = (0, job.table.count) if calls is None else calls
+    if not job.groups.synced:
+        # nothing is known on the host yet (a fused encode just queued): queue the '0'/'1' expansion on capacity bounds and
+        # bring the group count, the per-call offsets and the total bit count over in ONE small copy
+        cap = job._cap
+        if with_bits and not hasattr(job, "ascii"):
+            job.expand_code_capacity()
+        first = E.to_host([job.groups.seg_group_off, job.seg_outlier_off] + ([job.bit_off[cap:cap + 1]] if with_bits else []))
+        job.groups.set_host(first[0].copy())
+        job.sync_groups()
+        pre = (first[1].copy(), int(first[2][0]) if with_bits else 0)
+    else:
+        pre = None
     g0, g1 = job.segment_group_range(s0)[0], job.segment_group_range(s1 - 1)[1]
     d0, d1 = job.table.starts[s0], job.table.starts[s1 - 1] + job.table.specs[s1 - 1].n
-    small = [job.seg_outlier_off] + ([job.bit_off[g0:g0 + 1], job.bit_off[g1:g1 + 1]] if with_bits else [])
-    small = E.to_host(small)                                 # copies only
-    seg_out = small[0].copy()
+    if pre is not None and s0 == 0 and s1 == job.table.count:
+        seg_out = pre[0]
+        bit0, bit1 = 0, pre[1]
+    else:
+        small = [job.seg_outlier_off] + ([job.bit_off[g0:g0 + 1], job.bit_off[g1:g1 + 1]] if with_bits else [])
+        small = E.to_host(small)                                 # copies only
+        seg_out = small[0].copy()
+        bit0, bit1 = (int(small[1][0]), int(small[2][0])) if with_bits else (0, 0)
     o0, o1 = int(seg_out[s0]), int(seg_out[s1])
-    bit0, bit1 = (int(small[1][0]), int(small[2][0])) if with_bits else (0, 0)
     names = ["sample", "starts", "index", "outlier_idx", "outlier_q"]
     tensors = [job.sample[d0:d1], job.groups.starts[g0:g1 + 1], job.index[g0:g1], job.outlier_idx[o0:o1], job.outlier_q[o0:o1]]
     if with_bits:

@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_finish_dims(
 __global__ void __launch_bounds__(FRONT_THREADS) k_pack_elias(const uint32_t* __restrict__ index, const uint32_t* __restrict__ base,
                                                               const long long* __restrict__ ng_dev, long long n_tiles,
                                                               uint32_t* __restrict__ words, long long* __restrict__ bit_off,
-                                                              ull* __restrict__ pack_words) {
+                                                              ull* __restrict__ pack_words, long long cap) {
   __shared__ ull sm_scan[33];
   const int tid = threadIdx.x;
   const long long t = blockIdx.x;
@@ -624,7 +624,10 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_pack_elias(const uint32_t* __
     }
     running += tot;
   }
-  if (t == n_tiles - 1 && tid == 0) bit_off[ng] = (long long)running;
+  if (t == n_tiles - 1 && tid == 0) {
+    bit_off[cap] = (long long)running;      // the total also at a place the host knows before it knows the group count
+    bit_off[ng] = (long long)running;
+  }
 }
 
 }  // namespace cwq
@@ -735,7 +738,6 @@ int front_group(const float* q_loc, const float* q_scale, const float* p_loc, co
 int front_finish(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale, long long n,
                  const cwq_segment* segs, int n_seg, long long cap, const FrontPlan& p, const FrontWorkspace& w,
                  const cwq_is_buffers* b, cudaStream_t st) {
-  (void)cap;
   const long long* ng_dev = (const long long*)b->seg_group_off + n_seg;
   CWQ_CUDA(cudaMemsetAsync(b->bits, 0, b->bits_capacity_bytes, st));
   CWQ_CUDA(cudaMemsetAsync(w.pack_status, 0, TilePrefix<1>::words(p.n_tiles) * 8, st));
@@ -749,7 +751,7 @@ int front_finish(const float* q_loc, const float* q_scale, const float* p_loc, c
   trace_end(slot, st);
   slot = trace_begin(TR_PACK, st);
   k_pack_elias<<<(unsigned)p.n_tiles, FRONT_THREADS, 0, st>>>(b->index, w.base, ng_dev, p.n_tiles, (uint32_t*)b->bits,
-                                                             (long long*)b->bit_off, w.pack_status);
+                                                             (long long*)b->bit_off, w.pack_status, cap);
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   return CWQ_OK;

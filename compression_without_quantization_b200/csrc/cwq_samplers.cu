@@ -620,7 +620,10 @@ struct EliasDeliver {
   }
 };
 __global__ void k_bits_finish(long long* bit_off, long long ng, const long long* ng_dev, const ull* total) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) bit_off[ng_dev ? *ng_dev : ng] = (long long)*total;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    bit_off[ng] = (long long)*total;        // capacity slot: where the host finds the total before it knows the group count
+    bit_off[ng_dev ? *ng_dev : ng] = (long long)*total;
+  }
 }
 __global__ void __launch_bounds__(256) k_bswap_words(uint32_t* __restrict__ words, long long nw) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

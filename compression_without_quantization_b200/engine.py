@@ -32,8 +32,17 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def current_stream_ptr():
+    """cudaStream_t of torch's current stream as an int.  torch.cuda.current_stream() costs ~15 us in Python (it builds a
+    Stream object); the raw query is ~1 us, and a small encode makes a dozen of these calls."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(current_stream_ptr())
 
 
 def is_float32(dtype):
@@ -148,7 +157,7 @@ def _segment_table_on_device(raw, device):
     benchmark loop) reuse one upload; a new table goes through pinned memory with an asynchronous copy -- a pageable
     upload would block the host until everything already queued on the stream has run, which serialises the chunks of
     the batch pipeline."""
-    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0, raw)
+    key = (device.type, device.index, current_stream_ptr() if device.type == "cuda" else 0, raw)
     hit = _table_cache.get(key)
     if hit is not None:
         _table_cache.move_to_end(key)
@@ -170,7 +179,7 @@ def segment_table(specs, device):
     """SegmentTable of a tuple of specs, built once per (specs, device, stream): constructing one costs ~10 us per call of
     the batch in Python, which is what the GPU waits for at the start of a small encode."""
     dev = torch.device(device)
-    key = (tuple(specs), dev.type, dev.index, torch.cuda.current_stream().cuda_stream if dev.type == "cuda" else 0)
+    key = (tuple(specs), dev.type, dev.index, current_stream_ptr() if dev.type == "cuda" else 0)
     hit = _segment_tables.get(key)
     if hit is not None:
         _segment_tables.move_to_end(key)
@@ -469,6 +478,14 @@ class ISJob:
             max_size = max(int(np.diff(np.asarray(st)).max()) for st in self.forced_starts)
         _lib.call("cwq_is_encode", _ptr(self.coef), _ptr(self.groups.starts), _ptr(self.K), _ptr(self.groups.group_seed),
                   cap, self._ng_dev(), g0, g1, max_size, _ptr(self.index), _ptr(ws), wsb, _stream())
+        return self
+
+    def expand_code_capacity(self):
+        """Queue the '0'/'1' expansion of the packed code right behind the packing WITHOUT knowing the group count: the
+        buffer is sized by the capacity (42 bits per possible group), the kernel reads the bit count on the device (the
+        packing leaves it in the last slot of bit_off).  Lets the caller fetch every count in one small copy."""
+        cap = self._cap
+        self.ascii = device_bits_to_ascii(self.bits, 42 * cap, self.bit_off[cap:cap + 1])
         return self
 
     def expand_code_async(self):

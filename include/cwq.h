@@ -221,7 +221,9 @@ CWQ_API int cwq_unrescale(const float* best, const float* p_loc, const float* p_
 
 /* ---- index -> bitstream ----------------------------------------------------------------------
  * BIO:7-20 Elias-delta of index + 1, codes concatenated MSB-first into bytes (the order the '0'/'1'
- * string has in the reference, BIO:76-79).  bit_off[n_groups + 1] = bit offset of each code. */
+ * string has in the reference, BIO:76-79).  bit_off[n_groups + 1] = bit offset of each code; with a device-side group
+ * count the total is ALSO written to bit_off[n_groups] of the capacity (the last slot), where a host that does not know
+ * the count yet can read it. */
 CWQ_API size_t cwq_pack_workspace_bytes(int64_t n_groups);
 CWQ_API int cwq_elias_delta_pack(const uint32_t* index, int64_t n_groups, const int64_t* n_groups_dev, uint8_t* bits,
                          size_t bits_capacity_bytes, int64_t* bit_off, void* workspace, size_t workspace_bytes,
