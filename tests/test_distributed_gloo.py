@@ -77,6 +77,30 @@ def _worker(rank, world, port, q):
         work = D.is_work(job).numpy().astype(np.float64)
         shares = [work[job.shard_bounds[r]:job.shard_bounds[r + 1]].sum() / work.sum() for r in range(world)]
         assert max(shares) < 0.5 + work.max() / work.sum() + 1e-9
+        # ---- round 2: call ownership and the sliced upload (every rank brings 1/world of the inputs, one all-gather) ----
+        shard = D.make_is_shard()
+        sizes = [7, 300, 41, 300, 5, 300]
+        c0, c1 = shard.call_range(sizes)
+        ranges = [None] * world
+        dist.all_gather_object(ranges, (c0, c1))
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(sizes) and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        assert all(hi > lo for lo, hi in ranges)                       # contiguous, covering, non-empty
+        assert D.make_is_shard(results="all").call_range(sizes) == (0, len(sizes))
+
+        class N:                                                      # tfd.Normal stand-in
+            def __init__(self, loc, scale):
+                self.loc, self.scale = loc, scale
+        base = [torch.arange(sum(sizes), dtype=torch.float32) + 1000 * k for k in range(4)]   # one buffer per array
+        off = np.cumsum([0] + sizes)
+        targets = [N(base[0][off[i]:off[i + 1]], base[1][off[i]:off[i + 1]]) for i in range(len(sizes))]
+        proposals = [N(base[2][off[i]:off[i + 1]].numpy(), base[3][off[i]:off[i + 1]].numpy()) for i in range(len(sizes))]  # numpy too
+        assert shard.can_slice_uploads(targets, proposals)
+        got = shard.upload_sliced(targets, proposals, torch.device("cpu"))
+        assert all(torch.equal(got[k], base[k]) for k in range(4))   # every rank ends up with the whole arrays
+        scattered = [N(t.loc.clone(), t.scale.clone()) for t in targets]                     # separate buffers: a copy, same result
+        got2 = shard.upload_sliced(scattered, proposals, torch.device("cpu"))
+        assert all(torch.equal(got2[k], base[k]) for k in range(4))
+        assert not D.make_is_shard(slice_uploads=False).can_slice_uploads(targets, proposals)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
