@@ -344,6 +344,7 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
                 host = _host_views(job, with_bits=not return_indices, calls=(lo, hi))
             for s in range(lo, hi):
                 results[i][s] = _segment_result(job, s, host, return_indices)
+            job.release()                # downloads synchronised: the buffers may serve the next batch of this shape
         jobs[i] = None
 
     # Order on the compute stream: G0 S0 | G1 F0 S1 | G2 F1 S2 | ... : the grouping of the next chunk is queued behind the
@@ -392,7 +393,9 @@ def code_grouped_importance_sample_batch(targets, proposals, seed, n_bits_per_gr
     job = _encode_batch(targets, proposals, seed, n_bits_per_group, max_group_size_bits, dim_kl_bit_limit, "full",
                         shard=shard)
     host = _host_views(job, with_bits=not return_indices)
-    return [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+    out = [_segment_result(job, s, host, return_indices) for s in range(job.table.count)]
+    job.release()
+    return out
 
 
 def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_group, max_group_size_bits=4,
@@ -423,7 +426,9 @@ def code_grouped_importance_sample(sess, target, proposal, seed, n_bits_per_grou
     if return_indices_only:
         return tuple(np.int64(i) + 1 for i in job.host_indices(0))
     host = _host_views(job, with_bits=not return_indices)
-    return _segment_result(job, 0, host, return_indices)
+    out = _segment_result(job, 0, host, return_indices)
+    job.release()
+    return out
 
 
 def decode_grouped_importance_sample_batch(bitcodes, group_start_indices, proposals, seed, outlier_indices,

@@ -107,9 +107,11 @@ class ISShard:
         world, _ = self._world_rank()
         if not self.slice_uploads or world == 1:
             return False
-        arrays = [t.loc for t in targets] + [t.scale for t in targets] + [p.loc for p in proposals] + [p.scale for p in proposals]
-        return all((isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.float32) or
-                   (isinstance(a, np.ndarray) and a.dtype == np.float32) for a in arrays)
+        def host_f32(a):
+            return (isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.float32) or \
+                   (isinstance(a, np.ndarray) and a.dtype == np.float32)
+        return all(host_f32(t.loc) and host_f32(t.scale) for t in targets) and \
+            all(host_f32(p.loc) and host_f32(p.scale) for p in proposals)
 
     def upload_sliced(self, targets, proposals, dev):
         """The four flat input arrays of a run of calls on the device: this rank copies its 1/world slice of each from the
