@@ -217,6 +217,9 @@ def _host_views(job, with_bits, calls=None):
 # copies and the host-side bit formatting of one chunk overlap the scoring kernel of the next.
 PIPELINE_MIN_DIMS = 1 << 21
 PIPELINE_CHUNKS = 4
+# a sharded run slices the upload of a chunk across the ranks (+ one all-gather) only above this many dims: below it every
+# rank copies the whole chunk itself, which is faster than the collective's launch latency (the small FIRST chunk)
+SLICE_MIN_DIMS = 1 << 20
 
 
 def _chunk_weights(world):
@@ -290,7 +293,7 @@ def _encode_batch_pipelined(targets, proposals, specs, chunks, return_indices, s
     def upload(i):                                   # stage 1: a chunk's inputs on the copy stream
         a, b = chunks[i]
         with torch.cuda.stream(up):
-            if sliced:
+            if sliced and sum(sp.n for sp in specs[a:b]) >= SLICE_MIN_DIMS:
                 tensors = shard.upload_sliced(targets[a:b], proposals[a:b], dev)
             else:
                 tensors = _upload(targets[a:b], proposals[a:b], dev)
