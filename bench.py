@@ -363,6 +363,25 @@ def secondary_measurements(dev, n1, n2):
     out["drop-in latency, one image (level 2 then level 1, numpy in/out)"] = {
         "ms_median": float(np.median(lat)), "ms_min": float(np.min(lat)), "device_ms_both_levels_one_launch": dev_ms,
         "host_overhead_ms": float(np.median(lat)) - dev_ms}
+
+    # the decoder's side of the same image (pln.py:744,783): bitstream + group starts + outliers in, latents out
+    r2, r1 = one_image()
+
+    def decode_image():
+        a = cwq.decode_grouped_importance_sample(None, r2[1], [int(x) for x in r2[2][:-1]], Normal(d2[2], d2[3]), 20, SEED, r2[3][0], r2[3][1])
+        b = cwq.decode_grouped_importance_sample(None, r1[1], [int(x) for x in r1[2][:-1]], Normal(d1[2], d1[3]), 20, SEED, r1[3][0], r1[3][1])
+        return a, b
+    for _ in range(3):
+        dec = decode_image()
+    assert np.array_equal(dec[1].view(np.uint32), r1[0].view(np.uint32)) and np.array_equal(dec[0].view(np.uint32), r2[0].view(np.uint32))
+    dl = []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        decode_image()
+        dl.append(1e3 * (time.perf_counter() - t0))
+    out["drop-in decode latency, one image (both levels, bitstream in, numpy out)"] = {
+        "ms_median": float(np.median(dl)), "ms_min": float(np.min(dl)), "round_trip_exact": True,
+        "reference_published_decode_s_per_kodak_image": "41.9-49.0 (Compression.ipynb:306-309, hardware unstated)"}
     return out
 
 
