@@ -360,12 +360,28 @@ def secondary_measurements(dev, n1, n2):
         one_image()
         lat.append(1e3 * (time.perf_counter() - t0))
     dev_ms = out["configs[1] one 768x512 image, IS 20 bits"]["step_ms"]
+    # what the copies of that call sequence cost alone: the eight pageable numpy inputs up (the caller's arrays are not
+    # pinned), result-sized buffers down through pinned staging -- the part of the overhead no host code can remove
+    r2, r1 = one_image()
+    down_bytes = sum(x[0].nbytes + len(x[1]) + x[2].nbytes + x[3][0].nbytes + x[3][1].nbytes for x in (r2, r1))
+    down_dev = torch.empty(down_bytes, dtype=torch.uint8, device=dev)
+    floor = []
+    for _ in range(8):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for arrs in (d2, d1):
+            keep = [E.as_device_f32(x, dev) for x in arrs]
+            torch.cuda.synchronize()
+        E.to_host([down_dev])
+        floor.append(1e3 * (time.perf_counter() - t0))
     out["drop-in latency, one image (level 2 then level 1, numpy in/out)"] = {
         "ms_median": float(np.median(lat)), "ms_min": float(np.min(lat)), "device_ms_both_levels_one_launch": dev_ms,
-        "host_overhead_ms": float(np.median(lat)) - dev_ms}
+        "host_overhead_ms": float(np.median(lat)) - dev_ms,
+        "copies_alone_ms": float(np.median(floor)),
+        "copies_note": "%d B of pageable numpy inputs up in 8 copies, %d B of results down through pinned staging" % (
+            sum(x.nbytes for arrs in (d2, d1) for x in arrs), down_bytes)}
 
     # the decoder's side of the same image (pln.py:744,783): bitstream + group starts + outliers in, latents out
-    r2, r1 = one_image()
 
     def decode_image():
         a = cwq.decode_grouped_importance_sample(None, r2[1], [int(x) for x in r2[2][:-1]], Normal(d2[2], d2[3]), 20, SEED, r2[3][0], r2[3][1])

@@ -36,23 +36,43 @@ def balanced_ranges(work, world):
     return _bounds_from_cuts(_cuts_on_device(w, world).cpu().tolist(), n, world)
 
 
+def all_gather_ranges_(values, bounds, group=None):
+    """In place: `values` (1-D or [n, width]) holds this rank's rows [bounds[rank], bounds[rank+1]); on return it holds
+    every rank's rows.  The ranges are padded to the longest one so that ONE all_gather_into_tensor moves everything; the
+    rank's rows are copied once into their slot of the receive buffer, the collective gathers in place (send buffer ==
+    that slot, no separate send tensor), and one batched copy (torch.cat with out=) lays the ragged ranges back out."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return values
+    rank = dist.get_rank(group)
+    lens = [bounds[r + 1] - bounds[r] for r in range(world)]
+    longest = max(max(lens), 1)
+    recv = torch.empty((world, longest) + tuple(values.shape[1:]), dtype=values.dtype, device=values.device)
+    recv[rank, :lens[rank]].copy_(values[bounds[rank]:bounds[rank + 1]])
+    # NCCL gathers in place when the send buffer is the rank's slot of the receive buffer; gloo wants a separate input
+    send = recv[rank] if values.is_cuda else recv[rank].clone()
+    dist.all_gather_into_tensor(recv.view(-1), send.reshape(-1), group=group)
+    if bounds[world] == values.shape[0] and bounds[0] == 0 and values.is_contiguous():
+        torch.cat([recv[r, :lens[r]] for r in range(world)], 0, out=values)
+    else:
+        for r in range(world):
+            if r != rank and lens[r]:
+                values[bounds[r]:bounds[r + 1]].copy_(recv[r, :lens[r]])
+    return values
+
+
 def all_gather_ranges(local, bounds, group=None):
     """Every rank owns values[bounds[r]:bounds[r+1]] (passed as `local`, 1-D or [len, width]); returns the
-    full concatenation on every rank.  Ranges are padded to the longest one so a single
-    all_gather_into_tensor moves everything."""
+    full concatenation on every rank (all_gather_ranges_ on a fresh array)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
     rank = dist.get_rank(group)
-    lens = [bounds[r + 1] - bounds[r] for r in range(world)]
-    assert local.shape[0] == lens[rank], "local slice does not match this rank's range"
-    width = local.shape[1:]
-    longest = max(max(lens), 1)
-    send = torch.zeros((longest,) + tuple(width), dtype=local.dtype, device=local.device)
-    send[:lens[rank]] = local
-    recv = torch.empty((world * longest,) + tuple(width), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    return torch.cat([recv[r * longest:r * longest + lens[r]] for r in range(world)], 0)
+    assert local.shape[0] == bounds[rank + 1] - bounds[rank], "local slice does not match this rank's range"
+    full = torch.empty((bounds[world] - bounds[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    rel = [b - bounds[0] for b in bounds]
+    full[rel[rank]:rel[rank + 1]].copy_(local)
+    return all_gather_ranges_(full, rel, group)
 
 
 def row_blocks(sizes):
@@ -152,7 +172,7 @@ class ISShard:
     def _all_gather(self, job, bounds):
         _, rank = self._world_rank()
         # in place: the finishing stages of a fused job read job.index through the raw pointer taken at allocation
-        job.index.copy_(all_gather_ranges(job.index[bounds[rank]:bounds[rank + 1]], bounds, self.group))
+        all_gather_ranges_(job.index, bounds, self.group)
         job.shard_bounds = bounds
 
     def plan_async(self, job, side):
@@ -203,7 +223,7 @@ def make_greedy_shard(group=None):
         job.encode(bounds[rank], bounds[rank + 1])
         ns = job.n_steps
         idx = job.indices.view(-1, ns)
-        job.indices = all_gather_ranges(idx[bounds[rank]:bounds[rank + 1]], bounds, group).contiguous().view(-1)
+        all_gather_ranges_(idx, bounds, group)
         # the running samples of the other ranks' groups are rebuilt from the gathered indices
         job.decode()
         job.best_from_decode = True

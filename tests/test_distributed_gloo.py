@@ -59,6 +59,12 @@ def _worker(rank, world, port, q):
         assert full.tolist() == [3 * i for i in range(12)]
         local2 = torch.arange(bounds[rank], bounds[rank + 1], dtype=torch.int32)[:, None].repeat(1, 4)
         assert D.all_gather_ranges(local2, bounds)[:, 2].tolist() == list(range(12))
+        # the in-place form the shards use: own rows filled, everything else overwritten; an empty range is legal
+        for bnd in ([0, 5, 12], [0, 0, 12], [0, 12, 12]):
+            vals = torch.full((12, 3), -1, dtype=torch.int32)
+            vals[bnd[rank]:bnd[rank + 1]] = torch.arange(bnd[rank], bnd[rank + 1], dtype=torch.int32)[:, None] * 7
+            ret = D.all_gather_ranges_(vals, bnd)
+            assert ret is vals and vals[:, 1].tolist() == [7 * i for i in range(12)]
         # sharded importance sampler on a small problem
         rng = np.random.default_rng(5)
         n = 600
