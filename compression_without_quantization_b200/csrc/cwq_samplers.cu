@@ -111,10 +111,18 @@ __device__ __forceinline__ void is_score_quad(const float4* __restrict__ sc, int
   acc1 = __fmaf_rn(z[3], __fmaf_rn(c23.z, z[3], c23.w), acc1);
 }
 
+// the first pair of a quad only (its last two dims do not exist: unit_quads_half)
+__device__ __forceinline__ void is_score_pair(const float4* __restrict__ sc, int q, const float (&z)[4], float& acc0, float& acc1) {
+  const float4 c01 = sc[2 * q];
+  acc0 = __fmaf_rn(z[0], __fmaf_rn(c01.x, z[0], c01.y), acc0);
+  acc1 = __fmaf_rn(z[1], __fmaf_rn(c01.z, z[1], c01.w), acc1);
+}
+
 // candidates [kb, ke) of one group of NQ <= 4 quads (one unit), coefficients staged in this warp's shared slice.
 // Per candidate: 2 shared IMAD.WIDE (lane_shared) + 14 per block (rounds 3..9), min(NQ, 3) blocks; the
-// (seed, block) parts of rounds 0-2 live in registers (bc).
-template <int NQ>
+// (seed, block) parts of rounds 0-2 live in registers (bc).  HALF: the last quad holds one or two dims, its second
+// Box-Muller pair is skipped (a third of the 13-15-dim groups of the default configuration end that way).
+template <int NQ, bool HALF>
 __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
                                                int lane, float& best, uint32_t& bestk) {
   constexpr int NB = NQ < 3 ? NQ : 3;
@@ -125,8 +133,15 @@ __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, ui
     float acc0 = 0.0f, acc1 = 0.0f;
     if (NQ > 0) {
       const LaneShared ls = lane_shared(sseed, k);
-      unit_quads<(NQ > 0 ? NQ : 1)>(ls, [&](int b) { return bc[b]; },
-                                    [&](int q, const float (&z)[4]) { is_score_quad(sc, q, z, acc0, acc1); });
+      if (HALF) {
+        unit_quads_half<(NQ > 0 ? NQ : 1)>(ls, [&](int b) { return bc[b]; },
+                                           [&](int q, const float (&z)[4], int pairs) {
+                                             if (pairs == 2) is_score_quad(sc, q, z, acc0, acc1); else is_score_pair(sc, q, z, acc0, acc1);
+                                           });
+      } else {
+        unit_quads<(NQ > 0 ? NQ : 1)>(ls, [&](int b) { return bc[b]; },
+                                      [&](int q, const float (&z)[4]) { is_score_quad(sc, q, z, acc0, acc1); });
+      }
     }
     float s = __fadd_rn(acc0, acc1);
     if (s > best) { best = s; bestk = k; }
@@ -226,12 +241,16 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
         if (lane < 16) my_coef[lane] = lane < G ? coef[s + lane] : make_float2(0.0f, 0.0f);
         __syncwarp();
         const float4* sc = s_coef[warp];
-        switch ((G + 3) >> 2) {
-          case 0: is_score_range<0>(sc, sseed, kb, ke, lane, best, bestk); break;
-          case 1: is_score_range<1>(sc, sseed, kb, ke, lane, best, bestk); break;
-          case 2: is_score_range<2>(sc, sseed, kb, ke, lane, best, bestk); break;
-          case 3: is_score_range<3>(sc, sseed, kb, ke, lane, best, bestk); break;
-          default: is_score_range<4>(sc, sseed, kb, ke, lane, best, bestk); break;
+        switch ((G + 1) >> 1) {      // Box-Muller pairs of the row: an odd count leaves the last quad half empty
+          case 0: is_score_range<0, false>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 1: is_score_range<1, true>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 2: is_score_range<1, false>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 3: is_score_range<2, true>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 4: is_score_range<2, false>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 5: is_score_range<3, true>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 6: is_score_range<3, false>(sc, sseed, kb, ke, lane, best, bestk); break;
+          case 7: is_score_range<4, true>(sc, sseed, kb, ke, lane, best, bestk); break;
+          default: is_score_range<4, false>(sc, sseed, kb, ke, lane, best, bestk); break;
         }
       } else if (!SMALL && G <= 64) {
         const int nq = (G + 3) >> 2;

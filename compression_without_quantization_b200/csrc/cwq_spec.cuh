@@ -197,6 +197,37 @@ __device__ __forceinline__ void unit_quads(const LaneShared& ls, GetBC&& bc, F&&
   }
 }
 
+// The same for a unit whose LAST quad carries at most two dims (NP = 2 NQ - 1 Box-Muller pairs): the last quad's second
+// pair -- and, for NQ == 4, the harvest of its two words -- is never formed; f(quad, z, pairs) sees pairs == 1 there and
+// reads z[0], z[1] only.  The dims left out have zero coefficients in every caller, so the result is the same bits.
+template <int NQ, class GetBC, class F>
+__device__ __forceinline__ void unit_quads_half(const LaneShared& ls, GetBC&& bc, F&& f) {
+  constexpr int NB = NQ < 3 ? NQ : 3;
+  uint32_t v[2] = {0u, 0u};
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    uint32_t o[4];
+    stream_block_tail(ls, bc(b), o);
+    if (NQ == 4) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) v[i] = b == 0 ? o[i] : (b == 1 ? harvest01(v[i], o[i]) : harvest2(v[i], o[i]));
+    }
+    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (NQ < 4 && b == NB - 1) {
+      box_muller(o[0], o[1], z[0], z[1]);
+      f(b, z, 1);
+    } else {
+      box_muller_quad(o, z);
+      f(b, z, 2);
+    }
+  }
+  if (NQ == 4) {
+    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    box_muller(v[0], v[1], z[0], z[1]);
+    f(3, z, 1);
+  }
+}
+
 // All nq quads of candidate k's row: f(quad, z[4]) in quad order; bc(j) = BlockConst of row block j.
 template <class GetBC, class F>
 __device__ __forceinline__ void row_quads(const LaneShared& ls, int nq, GetBC&& bc, F&& f) {
