@@ -25,7 +25,15 @@ using ull = unsigned long long;
 constexpr int IS_THREADS = 256;
 constexpr int IS_WARPS = IS_THREADS / 32;
 constexpr int UNIT_CAND = 1024;  // candidates per unit
-constexpr int UNIT_BATCH = 4;    // units claimed per atomic
+#ifndef CWQ_UNIT_BATCH
+#define CWQ_UNIT_BATCH 4
+#endif
+// build-time knobs of tools/ab_variants.py (same results, different code generation)
+#ifndef CWQ_IS_MIN_BLOCKS
+#define CWQ_IS_MIN_BLOCKS 3
+#endif
+
+constexpr int UNIT_BATCH = CWQ_UNIT_BATCH;    // units claimed per atomic
 
 // The scored range of groups is [g0, g1).  Either end may live on the device (g0_dev / g1_dev non-null): g1_dev is the
 // group count of a synchronisation-free encode, (g0_dev, g1_dev) the range a rank computed for itself on the device;
@@ -123,8 +131,9 @@ __device__ __forceinline__ void is_score_pair(const float4* __restrict__ sc, int
 // (seed, block) parts of rounds 0-2 live in registers (bc).  HALF: the last quad holds one or two dims, its second
 // Box-Muller pair is skipped (a third of the 13-15-dim groups of the default configuration end that way).
 template <int NQ, bool HALF>
-__device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
-                                               int lane, float& best, uint32_t& bestk) {
+__device__ __forceinline__ ull is_score_range_impl(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke, int lane) {
+  float best = __uint_as_float(0xff800000u);
+  uint32_t bestk = 0xffffffffu;
   constexpr int NB = NQ < 3 ? NQ : 3;
   BlockConst bc[NB > 0 ? NB : 1];
 #pragma unroll
@@ -146,6 +155,14 @@ __device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, ui
     float s = __fadd_rn(acc0, acc1);
     if (s > best) { best = s; bestk = k; }
   }
+  return ((ull)__float_as_uint(best) << 32) | (ull)bestk;
+}
+template <int NQ, bool HALF>
+__device__ __forceinline__ void is_score_range(const float4* __restrict__ sc, uint32_t sseed, uint32_t kb, uint32_t ke,
+                                               int lane, float& best, uint32_t& bestk) {
+  const ull r = is_score_range_impl<NQ, HALF>(sc, sseed, kb, ke, lane);
+  best = __uint_as_float((uint32_t)(r >> 32));
+  bestk = (uint32_t)r;
 }
 
 // 16 < G <= 64: coefficients and the per-(seed, block) Philox constants staged in this warp's shared slice
@@ -184,10 +201,18 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
   }
 }
 
+constexpr double LOW_K_MAX_NATS = 12.0 * 0.6931471805599453 - 1.0;   // budgets up to 12 bits per group (CIS:181)
+
 // SMALL: every group has <= 16 dims (the reference defaults): only the register-resident path is compiled in,
 // which keeps the kernel at 64 registers / 4 resident CTAs per SM (measured best).
-template <bool SMALL>
-__global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
+// LOWK: the launch for small KL budgets (<= 12 bits per group: tens to hundreds of candidates, one unit per group).  The
+// per-group bookkeeping weighs as much as the scoring there, so this instantiation drops what it can: when every group is
+// exactly one unit (checked on the device: #units == #groups) the group of a unit needs no search and no unit prefix, and
+// the warp argmax is two REDUX instead of five 64-bit shuffle rounds.  Kept apart from the default instantiation on
+// purpose: ptxas schedules the 231-instruction candidate loop differently whenever the code around it changes, and the
+// default's schedule is the one measured fastest on the headline batch (tools/ab_variants.py).
+template <bool SMALL, bool LOWK>
+__global__ void __launch_bounds__(IS_THREADS, CWQ_IS_MIN_BLOCKS) k_is_score(const float2* __restrict__ coef, const long long* __restrict__ starts,
                                                          const int* __restrict__ K, const uint32_t* __restrict__ gseed,
                                                          GroupRange range, const ull* __restrict__ unit_off_any,
                                                          int unit_off_is_global, ull* __restrict__ counter,
@@ -202,6 +227,7 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
   const ull u_first = unit_off[0];
   const ull n_units = unit_off[ng];
   float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
+  const bool one_each = LOWK && (n_units - u_first) == (ull)ng;      // every group of the range is exactly one unit
   for (;;) {
     ull u = 0;
     if (lane == 0) u = atomicAdd(counter, (ull)UNIT_BATCH);
@@ -211,6 +237,7 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
     // group of unit u: the largest j with unit_off[j] <= u (unit_off is strictly increasing: every group has a unit).
     // 32-ary search, one probe per lane and round: ~4 rounds of one L2 access instead of 18 dependent ones.
     long long lo = 0, hi = ng - 1;
+    if (LOWK && one_each) lo = hi = (long long)(u - u_first);
     while (lo < hi) {
       const long long step = (hi - lo + 31) >> 5;
       long long probe = lo + (long long)(lane + 1) * step;
@@ -224,7 +251,9 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
     }
     long long j = lo;
     while (u < u_end) {
-      const ull off_j = unit_off[j], off_n = unit_off[j + 1];
+      ull off_j, off_n;
+      if (LOWK && one_each) { off_j = u_first + (ull)j; off_n = off_j + 1ull; }
+      else { off_j = unit_off[j]; off_n = unit_off[j + 1]; }
       const ull ue = u_end < off_n ? u_end : off_n;
       const long long g = g0 + j;
       const uint32_t Kg = (uint32_t)K[g];
@@ -266,9 +295,18 @@ __global__ void __launch_bounds__(IS_THREADS, 3) k_is_score(const float2* __rest
       } else if (!SMALL) {
         is_score_range_generic(coef + s, G, sseed, kb, ke, lane, best, bestk);
       }
+      // warp argmax as two REDUX: the largest orderable score, then the lowest index among the lanes that hold it -- the
+      // maximum of pack_key() over the lanes (0 = a lane without a candidate; orderable() of a real score is never 0)
+      if (LOWK) {
+      const uint32_t sb = bestk == 0xffffffffu ? 0u : orderable(best);
+      const uint32_t top = __reduce_max_sync(0xffffffffu, sb);
+      const uint32_t kmin = __reduce_min_sync(0xffffffffu, sb == top ? bestk : 0xffffffffu);
+      if (lane == 0 && top != 0u) atomicMax(&keys[g], ((ull)top << 32) | (ull)(~kmin));
+      } else {
       ull key = bestk == 0xffffffffu ? 0ull : pack_key(best, bestk);
       key = warp_max_key(key);
       if (lane == 0 && key != 0ull) atomicMax(&keys[g], key);
+      }
       u = ue;
       ++j;
     }
@@ -754,9 +792,9 @@ static int ensure_device_props() {
   CWQ_CUDA(cudaGetDevice(&dev));
   int sms = 0, bps = 0;
   CWQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<true>, IS_THREADS, 0));
+  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<true, false>, IS_THREADS, 0));
   g_is_blocks_per_sm = bps > 0 ? bps : 1;
-  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<false>, IS_THREADS, 0));
+  CWQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_is_score<false, false>, IS_THREADS, 0));
   g_is_blocks_per_sm_any = bps > 0 ? bps : 1;
   if (const char* e = getenv("CWQ_IS_BLOCKS_PER_SM")) {   // tuning knob: fewer resident CTAs than the occupancy limit
     int v = atoi(e);
@@ -814,7 +852,7 @@ extern "C" size_t cwq_is_encode_workspace_bytes(int64_t n_groups) {
 // `front` (may be null): the fused front end already holds the unit prefix over all groups, initialised keys and a counter
 static int is_encode_impl(const float* coef, const int64_t* starts, const int32_t* K, const uint32_t* group_seed, int64_t n_groups,
                           GroupRange range, int64_t max_group_size, uint32_t* index, void* workspace, size_t workspace_bytes,
-                          void* stream, const FrontWorkspace* front = nullptr) {
+                          void* stream, const FrontWorkspace* front = nullptr, bool low_k = false) {
   int rc = ensure_device_props();
   if (rc != CWQ_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -842,12 +880,17 @@ static int is_encode_impl(const float* coef, const int64_t* starts, const int32_
   }
   const int is_global = front ? 1 : 0;
   const int slot = trace_begin(TR_SCORE, st);
-  if (max_group_size <= 16)
-    k_is_score<true><<<g_sm_count * g_is_blocks_per_sm, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                              group_seed, range, unit_off, is_global, counter, keys);
-  else
-    k_is_score<false><<<g_sm_count * g_is_blocks_per_sm_any, IS_THREADS, 0, st>>>((const float2*)coef, (const long long*)starts, K,
-                                                                                   group_seed, range, unit_off, is_global, counter, keys);
+  const float2* cf = (const float2*)coef;
+  const long long* stt = (const long long*)starts;
+  if (max_group_size <= 16) {
+    const unsigned grid = g_sm_count * g_is_blocks_per_sm;
+    if (low_k) k_is_score<true, true><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+    else k_is_score<true, false><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+  } else {
+    const unsigned grid = g_sm_count * g_is_blocks_per_sm_any;
+    if (low_k) k_is_score<false, true><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+    else k_is_score<false, false><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+  }
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   const int slot_i = trace_begin(TR_INDEX, st);
@@ -1137,7 +1180,11 @@ extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, 
     if (stages & CWQ_STAGE_SCORE) {
       GroupRange range{0, cap, nullptr, (const long long*)ng_dev};
       if (b->score_range_dev) range = GroupRange{0, cap, (const long long*)b->score_range_dev, (const long long*)b->score_range_dev + 1};
-      rc = is_encode_impl(b->coef, b->starts, b->K, b->group_seed, cap, range, max_group_size, b->index, nullptr, 0, stream, &fw);
+      // small budgets everywhere in the batch -> the low-K instantiation of the scoring kernel (same results)
+      bool low_k = h_segments != nullptr;
+      for (int32_t i = 0; low_k && i < n_segments; ++i) low_k = h_segments[i].n_nats_per_group <= LOW_K_MAX_NATS;
+      rc = is_encode_impl(b->coef, b->starts, b->K, b->group_seed, cap, range, max_group_size, b->index, nullptr, 0, stream, &fw,
+                          low_k);
       if (rc != CWQ_OK) return rc;
     }
     if (stages & CWQ_STAGE_FINISH) {

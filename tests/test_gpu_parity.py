@@ -146,6 +146,41 @@ def test_prologue_and_candidate_counts_bit_exact(cwq, oracle, syn):
 # ------------------------------------------------------------------------------------------------
 # importance sampler: full parity with injected draws, round trips
 # ------------------------------------------------------------------------------------------------
+def test_is_every_group_size_bit_exact(cwq, oracle):
+    """One group of every size 1 .. 18 with ~1100 candidates (two scoring units): each size takes its own instantiation of
+    the scoring loop -- full quads, a last quad with one Box-Muller pair only (sizes 4q + 1, 4q + 2), the > 16-dim path."""
+    rng = np.random.default_rng(3)
+    for G in range(1, 19):
+        p_loc = rng.normal(size=G).astype(np.float32)
+        p_scale = (0.5 + rng.random(G)).astype(np.float32)
+        d = np.sqrt(2.0 * 7.0 / G) * rng.choice([-1.0, 1.0], size=G)           # KL(t||p) = 7 nats -> K = 1097
+        t_loc = (p_loc + p_scale * d).astype(np.float32)
+        t_scale = p_scale.copy()
+        best, ip1 = cwq.code_importance_sample(t_loc, t_scale, p_loc, p_scale, 20, 1000 + G, return_index_only=True)
+        obest, oip1 = oracle.code_importance_sample(t_loc, t_scale, p_loc, p_scale, 20, 1000 + G, return_index_only=True,
+                                                    normal_source=_src(cwq))
+        assert int(ip1) == int(oip1), "group size {}".format(G)
+        assert np.array_equal(best.view(np.uint32), obest.view(np.uint32)), "group size {}".format(G)
+
+
+def test_low_budget_kernel_with_multi_unit_groups(cwq, oracle, syn):
+    """Budgets <= 12 bits take the low-K instantiation of the scoring kernel; with a per-dim limit above the budget some
+    one-dim groups still need several 1024-candidate units, which switches its one-unit-per-group shortcut off."""
+    q_loc, q_scale, p_loc, p_scale = syn.synthetic_posterior(400, 11)
+    q_loc = q_loc.copy()
+    q_loc[::37] += np.float32(4.0) * p_scale[::37]          # ~8 nats each: alone over an 8-bit budget, K ~ 3000
+    for seed, with_big in ((5, True), (6, False)):
+        ql = q_loc if with_big else syn.synthetic_posterior(400, 11)[0]
+        got = cwq.code_grouped_importance_sample(None, syn.Normal(ql, q_scale), syn.Normal(p_loc, p_scale), seed, 8, 4, 14)
+        want = oracle.code_grouped_importance_sample(None, oracle.Normal(ql, q_scale), oracle.Normal(p_loc, p_scale), seed, 8, 4, 14,
+                                                     normal_source=_src(cwq))
+        assert np.array_equal(got[2], want[2]) and got[1] == want[1]
+        assert np.array_equal(got[0].view(np.uint32), want[0].view(np.uint32))
+    K = oracle.group_totals(oracle.is_prologue(q_loc, q_scale, p_loc, p_scale, 14)[2],
+                            oracle.group(oracle.is_prologue(q_loc, q_scale, p_loc, p_scale, 14)[2], 8, 4, True))[1]
+    assert K.max() > 1024 and (K <= 1024).sum() > 10          # the case is what the docstring says
+
+
 @pytest.mark.parametrize("n,bits,m,limit,nontrivial,seed", [
     (700, 12, 4, 10, False, 42), (500, 10, 2, 8, True, 7), (300, 14, 3, 12, True, 123456789), (64, 8, 5, 6, False, 0),
 ])
