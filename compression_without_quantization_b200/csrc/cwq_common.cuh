@@ -43,6 +43,30 @@ enum TraceKind { TR_SCORE = 0, TR_FRONT_TILES = 1, TR_FRONT_CHAIN = 2, TR_FRONT_
 int trace_begin(int kind, cudaStream_t st);
 void trace_end(int slot, cudaStream_t st);
 
+// Programmatic dependent launch along the kernel chain of the fused pipeline (tiles -> chain -> groups -> prefix -> score ->
+// index -> finish -> pack): a kernel launched with the attribute may become resident while its predecessor on the stream is
+// still running; it must call pdl_wait() before it touches anything the predecessor (or anything earlier on the stream)
+// wrote, and the predecessor lets it in early with pdl_trigger().  Launch latency and grid ramp-up then overlap the tail of
+// the previous kernel -- what a step of eight 10-30 us kernels is made of.  CWQ_PDL=0 in the environment turns it off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // bump allocator over the caller's workspace

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_tiles(
     float* __restrict__ kl, float2* __restrict__ coef, uint8_t* __restrict__ mask, uint8_t* __restrict__ hop,
     int* __restrict__ seg_first, uint8_t* __restrict__ maps, uint16_t* __restrict__ counts, uint32_t* __restrict__ rows,
     uint32_t* __restrict__ tile_out, const int* __restrict__ tile_segment) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = T >> 5;
   float* kl_s = reinterpret_cast<float*>(smem_raw);                                   // [T + E]
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_front_chain(
     uint32_t* __restrict__ base, uint32_t* __restrict__ tile_out_off, long long* __restrict__ starts,
     long long* __restrict__ seg_group_off, long long* __restrict__ seg_outlier_off, ull* __restrict__ status,
     ull* __restrict__ scalars) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint8_t* maps_s = smem_raw;                                        // [n_tiles * E]
   const long long nb = (n_tiles + CHAIN_BLOCK - 1) / CHAIN_BLOCK;
@@ -330,6 +334,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
     const long long* __restrict__ seg_group_off, long long* __restrict__ starts, int* __restrict__ gid,
     uint32_t* __restrict__ group_seed, float* __restrict__ total_kl, int* __restrict__ K, ull* __restrict__ keys,
     ull* __restrict__ unit_off, ull* __restrict__ work_off, ull* __restrict__ prefix_words, const int* __restrict__ tile_segment) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = T >> 5;
   float* kl_s = reinterpret_cast<float*>(smem_raw);                        // [T + E] the tile's kl and the halo behind it
@@ -444,6 +450,8 @@ constexpr int PREFIX_THREADS = 64;
 __global__ void __launch_bounds__(PREFIX_THREADS) k_front_prefix(long long n_tiles, const uint32_t* __restrict__ base,
                                                                  const long long* __restrict__ ng_dev, ull* __restrict__ unit_off,
                                                                  ull* __restrict__ work_off, ull* __restrict__ prefix_words) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ ull sm[2 * 33];
   const long long t = blockIdx.x;
   const TilePrefix<2> tp = TilePrefix<2>::carve(prefix_words, n_tiles);
@@ -495,6 +503,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_finish_dims(
     float* __restrict__ sample, long long* __restrict__ outlier_idx, uint16_t* __restrict__ outlier_q,
     long long* __restrict__ seg_outlier_off, const uint32_t* __restrict__ base, const long long* __restrict__ ng_dev,
     long long n_tiles, ull* __restrict__ pack_words, const int* __restrict__ tile_segment) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t sm_scan[33];
   __shared__ ull sm_bits[33];
   const int tid = threadIdx.x;
@@ -602,6 +612,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_pack_elias(const uint32_t* __
                                                               const long long* __restrict__ ng_dev, long long n_tiles,
                                                               uint32_t* __restrict__ words, long long* __restrict__ bit_off,
                                                               ull* __restrict__ pack_words, long long cap) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ ull sm_scan[33];
   const int tid = threadIdx.x;
   const long long t = blockIdx.x;
@@ -710,28 +722,38 @@ int front_group(const float* q_loc, const float* q_scale, const float* p_loc, co
   const int* ts = b->tile_segment;
   const long long* ng_dev = (const long long*)b->seg_group_off + n_seg;
   int slot = trace_begin(TR_FRONT_TILES, st);
-  k_front_tiles<<<(unsigned)p.n_tiles, FRONT_THREADS, p.smem_tiles, st>>>(
-      q_loc, q_scale, p_loc, p_scale, n, segs, n_seg, p.T, p.E, b->kl, (float2*)b->coef, b->mask, w.hop, w.seg_first, w.maps,
-      w.counts, w.rows, w.tile_out, ts);
+  CWQ_CUDA(launch_chain(k_front_tiles, dim3((unsigned)p.n_tiles), dim3(FRONT_THREADS), p.smem_tiles, st, q_loc, q_scale, p_loc,
+                        p_scale, (long long)n, segs, n_seg, p.T, p.E, b->kl, (float2*)b->coef, b->mask, w.hop, w.seg_first, w.maps,
+                        w.counts, w.rows, w.tile_out, ts));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   slot = trace_begin(TR_FRONT_CHAIN, st);
-  k_front_chain<<<1, CHAIN_THREADS, p.smem_chain, st>>>(n, segs, n_seg, p.T, p.E, p.n_tiles, w.seg_first, w.maps, w.counts, w.rows,
-                                                       w.tile_out, w.entry, w.base, w.tile_out_off, (long long*)b->starts,
-                                                       (long long*)b->seg_group_off, (long long*)b->seg_outlier_off, w.status,
-                                                       w.scalars);
+  CWQ_CUDA(launch_chain(k_front_chain, dim3(1), dim3(CHAIN_THREADS), p.smem_chain, st, (long long)n, segs, n_seg, p.T, p.E, p.n_tiles,
+                        w.seg_first, w.maps, w.counts, w.rows, w.tile_out, w.entry, w.base, w.tile_out_off, (long long*)b->starts,
+                        (long long*)b->seg_group_off, (long long*)b->seg_outlier_off, w.status, w.scalars));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   slot = trace_begin(TR_FRONT_GROUPS, st);
-  k_front_groups<<<(unsigned)p.n_tiles, FRONT_THREADS, p.smem_groups, st>>>(
-      n, segs, n_seg, p.T, p.E, p.n_tiles, b->kl, w.hop, w.seg_first, w.rows, w.entry, w.base, (const long long*)b->seg_group_off,
-      (long long*)b->starts, b->gid, b->group_seed, b->total_kl, b->K, w.keys, w.unit_off, w.work_off, w.status, ts);
+  CWQ_CUDA(launch_chain(k_front_groups, dim3((unsigned)p.n_tiles), dim3(FRONT_THREADS), p.smem_groups, st, (long long)n, segs, n_seg,
+                        p.T, p.E, p.n_tiles, b->kl, w.hop, w.seg_first, w.rows, w.entry, w.base, (const long long*)b->seg_group_off,
+                        (long long*)b->starts, b->gid, b->group_seed, b->total_kl, b->K, w.keys, w.unit_off, w.work_off, w.status,
+                        ts));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   slot = trace_begin(TR_FRONT_PREFIX, st);
-  k_front_prefix<<<(unsigned)p.n_tiles, PREFIX_THREADS, 0, st>>>(p.n_tiles, w.base, ng_dev, w.unit_off, w.work_off, w.status);
+  CWQ_CUDA(launch_chain(k_front_prefix, dim3((unsigned)p.n_tiles), dim3(PREFIX_THREADS), 0, st, p.n_tiles, w.base, ng_dev, w.unit_off,
+                        w.work_off, w.status));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
+  return CWQ_OK;
+}
+
+// zeroes what the FINISH kernels OR / publish into (the bitstream, the packing kernel's tile words).  Nothing between the
+// GROUP stage and FINISH touches them, so a call that runs all stages clears them first and keeps its kernel chain unbroken
+// (a memset between two kernels ends a programmatic dependent launch chain).
+int front_finish_clear(const FrontPlan& p, const FrontWorkspace& w, const cwq_is_buffers* b, cudaStream_t st) {
+  CWQ_CUDA(cudaMemsetAsync(b->bits, 0, b->bits_capacity_bytes, st));
+  CWQ_CUDA(cudaMemsetAsync(w.pack_status, 0, TilePrefix<1>::words(p.n_tiles) * 8, st));
   return CWQ_OK;
 }
 
@@ -739,19 +761,16 @@ int front_finish(const float* q_loc, const float* q_scale, const float* p_loc, c
                  const cwq_segment* segs, int n_seg, long long cap, const FrontPlan& p, const FrontWorkspace& w,
                  const cwq_is_buffers* b, cudaStream_t st) {
   const long long* ng_dev = (const long long*)b->seg_group_off + n_seg;
-  CWQ_CUDA(cudaMemsetAsync(b->bits, 0, b->bits_capacity_bytes, st));
-  CWQ_CUDA(cudaMemsetAsync(w.pack_status, 0, TilePrefix<1>::words(p.n_tiles) * 8, st));
   int slot = trace_begin(TR_FINISH_DIMS, st);
-  k_finish_dims<<<(unsigned)p.n_tiles, FRONT_THREADS, 0, st>>>(n, segs, n_seg, p.T, q_loc, q_scale, p_loc, p_scale, b->mask,
-                                                              (const long long*)b->starts, b->group_seed, b->gid, b->index,
-                                                              w.tile_out_off, b->sample, (long long*)b->outlier_idx, b->outlier_q,
-                                                              (long long*)b->seg_outlier_off, w.base, ng_dev, p.n_tiles,
-                                                              w.pack_status, b->tile_segment);
+  CWQ_CUDA(launch_chain(k_finish_dims, dim3((unsigned)p.n_tiles), dim3(FRONT_THREADS), 0, st, (long long)n, segs, n_seg, p.T, q_loc,
+                        q_scale, p_loc, p_scale, b->mask, (const long long*)b->starts, b->group_seed, b->gid, b->index,
+                        w.tile_out_off, b->sample, (long long*)b->outlier_idx, b->outlier_q, (long long*)b->seg_outlier_off, w.base,
+                        ng_dev, p.n_tiles, w.pack_status, b->tile_segment));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   slot = trace_begin(TR_PACK, st);
-  k_pack_elias<<<(unsigned)p.n_tiles, FRONT_THREADS, 0, st>>>(b->index, w.base, ng_dev, p.n_tiles, (uint32_t*)b->bits,
-                                                             (long long*)b->bit_off, w.pack_status, cap);
+  CWQ_CUDA(launch_chain(k_pack_elias, dim3((unsigned)p.n_tiles), dim3(FRONT_THREADS), 0, st, b->index, w.base, ng_dev, p.n_tiles,
+                        (uint32_t*)b->bits, (long long*)b->bit_off, w.pack_status, (long long)cap));
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   return CWQ_OK;

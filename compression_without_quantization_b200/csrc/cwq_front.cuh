@@ -46,6 +46,7 @@ bool front_carve(void* workspace, size_t bytes, long long n, int n_seg, long lon
 int front_group(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale, long long n,
                 const cwq_segment* segs, int n_seg, const FrontPlan& plan, const FrontWorkspace& w, const cwq_is_buffers* b,
                 cudaStream_t st);
+int front_finish_clear(const FrontPlan& plan, const FrontWorkspace& w, const cwq_is_buffers* b, cudaStream_t st);
 int front_finish(const float* q_loc, const float* q_scale, const float* p_loc, const float* p_scale, long long n,
                  const cwq_segment* segs, int n_seg, long long cap, const FrontPlan& plan, const FrontWorkspace& w,
                  const cwq_is_buffers* b, cudaStream_t st);

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(IS_THREADS, CWQ_IS_MIN_BLOCKS) k_is_score(cons
                                                          GroupRange range, const ull* __restrict__ unit_off_any,
                                                          int unit_off_is_global, ull* __restrict__ counter,
                                                          ull* __restrict__ keys) {
+  pdl_wait();      // no early trigger: the kernel fills the SMs for most of a step, what follows moves in as its CTAs retire
   __shared__ float4 s_coef[IS_WARPS][SMALL ? 8 : 32];   // 16 or 64 (a, b) pairs per warp
   __shared__ uint4 s_quad[IS_WARPS][SMALL ? 1 : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,9 +314,15 @@ __global__ void __launch_bounds__(IS_THREADS, CWQ_IS_MIN_BLOCKS) k_is_score(cons
   }
 }
 
-__global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, GroupRange range, uint32_t* __restrict__ index) {
-  const long long g = range.begin() + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < range.end()) index[g] = key_index(keys[g]);
+// also hands the unit counter back at zero for the next scoring launch on these buffers
+__global__ void __launch_bounds__(256) k_is_index(const ull* __restrict__ keys, GroupRange range, uint32_t* __restrict__ index,
+                                                  ull* __restrict__ counter) {
+  pdl_wait();
+  pdl_trigger();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ull;
+  // grid-stride: the host often knows only the capacity of the range (its end lives on the device)
+  const long long end = range.end(), stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = range.begin() + (long long)blockIdx.x * blockDim.x + threadIdx.x; g < end; g += stride) index[g] = key_index(keys[g]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -712,17 +719,21 @@ __global__ void __launch_bounds__(256) k_fixed_unpack(const uint8_t* __restrict_
 constexpr int ASCII_THREADS = 64;
 __global__ void __launch_bounds__(ASCII_THREADS) k_bits_to_ascii(const uint8_t* __restrict__ bits, long long n_bytes,
                                                        const long long* __restrict__ n_bits_dev, uint2* __restrict__ ascii) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (n_bits_dev) { const long long nb = (*n_bits_dev + 7) >> 3; n_bytes = nb < n_bytes ? nb : n_bytes; }
-  if (i >= n_bytes) return;
-  const uint32_t b = bits[i];
-  uint32_t lo = 0x30303030u, hi = 0x30303030u;   // characters 0-3 (bits 7..4) and 4-7 (bits 3..0), little-endian words
+  // grid-stride: with the count on the device the host sizes the launch by the capacity, usually many times the code
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += stride) {
+    const uint32_t b = bits[i];
+    uint32_t lo = 0x30303030u, hi = 0x30303030u;   // characters 0-3 (bits 7..4) and 4-7 (bits 3..0), little-endian words
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    lo |= ((b >> (7 - c)) & 1u) << (8 * c);
-    hi |= ((b >> (3 - c)) & 1u) << (8 * c);
+    for (int c = 0; c < 4; ++c) {
+      lo |= ((b >> (7 - c)) & 1u) << (8 * c);
+      hi |= ((b >> (3 - c)) & 1u) << (8 * c);
+    }
+    ascii[i] = make_uint2(lo, hi);
   }
-  ascii[i] = make_uint2(lo, hi);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -862,8 +873,7 @@ static int is_encode_impl(const float* coef, const int64_t* starts, const int32_
   if (front) {
     unit_off = front->unit_off;
     keys = front->keys;
-    counter = front->scalars + FRONT_SCORE_COUNTER;
-    CWQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(ull), st));
+    counter = front->scalars + FRONT_SCORE_COUNTER;      // zero: k_front_chain cleared it, k_is_index clears it after every scoring
   } else {
     Workspace ws(workspace, workspace_bytes);
     unit_off = ws.take<ull>((size_t)span + 1);
@@ -882,19 +892,25 @@ static int is_encode_impl(const float* coef, const int64_t* starts, const int32_
   const int slot = trace_begin(TR_SCORE, st);
   const float2* cf = (const float2*)coef;
   const long long* stt = (const long long*)starts;
+  const dim3 blk(IS_THREADS);
+  const int ug = is_global;
+  cudaError_t le;
   if (max_group_size <= 16) {
-    const unsigned grid = g_sm_count * g_is_blocks_per_sm;
-    if (low_k) k_is_score<true, true><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
-    else k_is_score<true, false><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+    const dim3 grid(g_sm_count * g_is_blocks_per_sm);
+    le = low_k ? launch_chain(k_is_score<true, true>, grid, blk, 0, st, cf, stt, K, group_seed, range, (const ull*)unit_off, ug, counter, keys)
+               : launch_chain(k_is_score<true, false>, grid, blk, 0, st, cf, stt, K, group_seed, range, (const ull*)unit_off, ug, counter, keys);
   } else {
-    const unsigned grid = g_sm_count * g_is_blocks_per_sm_any;
-    if (low_k) k_is_score<false, true><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
-    else k_is_score<false, false><<<grid, IS_THREADS, 0, st>>>(cf, stt, K, group_seed, range, unit_off, is_global, counter, keys);
+    const dim3 grid(g_sm_count * g_is_blocks_per_sm_any);
+    le = low_k ? launch_chain(k_is_score<false, true>, grid, blk, 0, st, cf, stt, K, group_seed, range, (const ull*)unit_off, ug, counter, keys)
+               : launch_chain(k_is_score<false, false>, grid, blk, 0, st, cf, stt, K, group_seed, range, (const ull*)unit_off, ug, counter, keys);
   }
+  CWQ_CUDA(le);
   CWQ_LAUNCH_CHECK();
   trace_end(slot, st);
   const int slot_i = trace_begin(TR_INDEX, st);
-  k_is_index<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(keys, range, index);
+  const long long index_blocks = (span + 255) / 256, index_cap = 4LL * g_sm_count;
+  CWQ_CUDA(launch_chain(k_is_index, dim3((unsigned)(index_blocks < index_cap ? index_blocks : index_cap)), dim3(256), 0, st,
+                        (const ull*)keys, range, index, counter));
   CWQ_LAUNCH_CHECK();
   trace_end(slot_i, st);
   return CWQ_OK;
@@ -1128,6 +1144,11 @@ __global__ void k_shard_bounds_from_prefix(const ull* __restrict__ work_off, con
   bounds[r] = lo + 1;
 }
 
+bool pdl_enabled() {
+  const char* e = getenv("CWQ_PDL");
+  return !e || atoi(e) != 0;
+}
+
 static bool g_front_enabled = true;
 }  // namespace cwq
 
@@ -1173,6 +1194,11 @@ extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, 
       return CWQ_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const bool clear_first = (stages & CWQ_STAGE_GROUP) && (stages & CWQ_STAGE_FINISH);
+    if (clear_first) {
+      rc = front_finish_clear(plan, fw, b, st);
+      if (rc != CWQ_OK) return rc;
+    }
     if (stages & CWQ_STAGE_GROUP) {
       rc = front_group(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, plan, fw, b, st);
       if (rc != CWQ_OK) return rc;
@@ -1188,6 +1214,10 @@ extern "C" int cwq_is_encode_pipeline(const float* q_loc, const float* q_scale, 
       if (rc != CWQ_OK) return rc;
     }
     if (stages & CWQ_STAGE_FINISH) {
+      if (!clear_first) {
+        rc = front_finish_clear(plan, fw, b, st);
+        if (rc != CWQ_OK) return rc;
+      }
       rc = front_finish(q_loc, q_scale, p_loc, p_scale, n, segments, n_segments, cap, plan, fw, b, st);
       if (rc != CWQ_OK) return rc;
     }
@@ -1251,8 +1281,11 @@ extern "C" int cwq_bits_to_ascii(const uint8_t* bits, int64_t n_bits, const int6
   CWQ_REQUIRE((reinterpret_cast<uintptr_t>(ascii) & 7u) == 0, "ascii must be 8-byte aligned");
   if (n_bits == 0) return CWQ_OK;
   const long long n_bytes = (n_bits + 7) / 8;
-  k_bits_to_ascii<<<(unsigned)((n_bytes + ASCII_THREADS - 1) / ASCII_THREADS), ASCII_THREADS, 0, (cudaStream_t)stream>>>(bits, n_bytes, (const long long*)n_bits_dev,
-                                                                                      reinterpret_cast<uint2*>(ascii));
+  int rc = ensure_device_props();
+  if (rc != CWQ_OK) return rc;
+  const long long blocks = (n_bytes + ASCII_THREADS - 1) / ASCII_THREADS, most = 32LL * g_sm_count;
+  CWQ_CUDA(launch_chain(k_bits_to_ascii, dim3((unsigned)(blocks < most ? blocks : most)), dim3(ASCII_THREADS), 0, (cudaStream_t)stream,
+                        bits, n_bytes, (const long long*)n_bits_dev, reinterpret_cast<uint2*>(ascii)));
   CWQ_LAUNCH_CHECK();
   return CWQ_OK;
 }
