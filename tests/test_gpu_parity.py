@@ -163,6 +163,22 @@ def test_is_every_group_size_bit_exact(cwq, oracle):
         assert np.array_equal(best.view(np.uint32), obest.view(np.uint32)), "group size {}".format(G)
 
 
+def test_dependent_launch_chain_changes_nothing(cwq, syn, monkeypatch):
+    """The fused pipeline launches its kernels as a programmatic-dependent-launch chain (every kernel waits on
+    griddepcontrol before it reads); CWQ_PDL=0 launches them fully serialised.  Same results either way, at sizes with one
+    and with many tiles, and over repeated calls on recycled buffers."""
+    for n, bits, m, limit in ((3000, 12, 4, 10), (70000, 16, 4, 14), (2304, 20, 2, 16)):
+        q_loc, q_scale, p_loc, p_scale = syn.synthetic_posterior(n, 21, True)
+        runs = []
+        for pdl in ("0", "1", "1", "0"):
+            monkeypatch.setenv("CWQ_PDL", pdl)
+            runs.append(cwq.code_grouped_importance_sample(None, syn.Normal(q_loc, q_scale), syn.Normal(p_loc, p_scale), 9, bits, m, limit))
+        for r in runs[1:]:
+            assert r[1] == runs[0][1] and np.array_equal(r[2], runs[0][2])
+            assert np.array_equal(r[0].view(np.uint32), runs[0][0].view(np.uint32))
+            assert np.array_equal(r[3][0], runs[0][3][0]) and np.array_equal(r[3][1], runs[0][3][1])
+
+
 def test_low_budget_kernel_with_multi_unit_groups(cwq, oracle, syn):
     """Budgets <= 12 bits take the low-K instantiation of the scoring kernel; with a per-dim limit above the budget some
     one-dim groups still need several 1024-candidate units, which switches its one-unit-per-group shortcut off."""
