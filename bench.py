@@ -383,9 +383,13 @@ def secondary_measurements(dev, n1, n2):
 
     # the decoder's side of the same image (pln.py:744,783): bitstream + group starts + outliers in, latents out
 
+    # the caller owns the group-start lists (pln.py:735-741, 767-770 builds them from the decoded group sizes); the decoder
+    # appends N to the list it is given (CIS:294), so every call gets its own copy
+    starts2, starts1 = r2[2][:-1].tolist(), r1[2][:-1].tolist()
+
     def decode_image():
-        a = cwq.decode_grouped_importance_sample(None, r2[1], [int(x) for x in r2[2][:-1]], Normal(d2[2], d2[3]), 20, SEED, r2[3][0], r2[3][1])
-        b = cwq.decode_grouped_importance_sample(None, r1[1], [int(x) for x in r1[2][:-1]], Normal(d1[2], d1[3]), 20, SEED, r1[3][0], r1[3][1])
+        a = cwq.decode_grouped_importance_sample(None, r2[1], list(starts2), Normal(d2[2], d2[3]), 20, SEED, r2[3][0], r2[3][1])
+        b = cwq.decode_grouped_importance_sample(None, r1[1], list(starts1), Normal(d1[2], d1[3]), 20, SEED, r1[3][0], r1[3][1])
         return a, b
     for _ in range(3):
         dec = decode_image()

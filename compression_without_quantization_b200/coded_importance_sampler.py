@@ -446,7 +446,7 @@ def decode_grouped_importance_sample_batch(bitcodes, group_start_indices, propos
     p_scale = [E.as_device_f32(p.scale, dev, "Proposal") for p in proposals]
     sizes = [int(x.numel()) for x in p_loc]
     specs = [E.SegmentSpec(sizes[i], seeds[i], 1.0, 0, float("inf"), True) for i in range(ns)]
-    table = E.SegmentTable(specs, dev)
+    table = E.segment_table(specs, dev)          # cached per (specs, device, stream): a codec decodes image after image
     groups = E._forced_groups(group_start_indices, table, dev)
     idx_parts = []
     for s in range(ns):

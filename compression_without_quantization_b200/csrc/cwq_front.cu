@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
   uint32_t* node_pre = seg_w + W;                                          // [W] nodes before each word
   uint32_t* seg_pre = node_pre + W;                                        // [W]
   uint8_t* hop_s = reinterpret_cast<uint8_t*>(seg_pre + W);                // [T]
+  uint16_t* slot_s = reinterpret_cast<uint16_t*>(hop_s + T);               // [2 T] the tile's groups in order: start dim | 0x8000 for a chain node
   __shared__ ull sm_scan[2 * 33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t = blockIdx.x;
@@ -382,61 +383,70 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_groups(
   }
   __syncthreads();
 
-  // each thread owns D consecutive dims: thread order == group order, and a thread's groups have consecutive indices
+  // Pass 1, one thread per D consecutive dims (cheap, uniform): the group of every dim, and the tile's groups laid out in
+  // order as a slot list -- slot = chain nodes + segment starts before the dim, which the popcount prefixes give without
+  // atomics; a dim that is both (a segment whose first dim alone is over the budget: empty forced group, CIS:183-204)
+  // takes two slots, the forced group first.
   const int D = T / FRONT_THREADS;
   const int li0 = tid * D;
-  ull my_units = 0, my_work = 0;
-  long long g_first = -1;
-  int g_count = 0;
+  const bool one_seg = slo == shi;
   if (li0 < lim) {
     const int w0 = li0 >> 5, b0 = li0 & 31;
     const uint32_t below = (1u << b0) - 1u;
     uint32_t nodes = node_pre[w0] + __popc(node_w[w0] & below);     // chain nodes / segment starts strictly before li0
     uint32_t sstarts = seg_pre[w0] + __popc(seg_w[w0] & below);
-    const bool one_seg = slo == shi;
     for (int r = 0; r < D && li0 + r < lim; ++r) {
       const int li = li0 + r;
       const uint32_t is_node = (node_w[li >> 5] >> (li & 31)) & 1u, is_seg = (seg_w[li >> 5] >> (li & 31)) & 1u;
-      if (is_node | is_seg) {
-        const int s = one_seg ? slo : find_segment_between(segs, slo, shi, tile0 + li);
-        const cwq_segment& sg = segs[s];
-        const uint32_t seed0 = sg.seed;
-        const long long goff = seg_group_off[s];
-        const long long seg_end_l = sg.end - tile0;
-        for (int which = 0; which < 2; ++which) {      // 0: the segment's forced first group, 1: the chain node's group
-          if (which == 0 ? !is_seg : !is_node) continue;
-          const long long g = (long long)B + nodes + sstarts + (which == 1 ? is_seg : 0u);
-          // a node's group ends at the next node -- or at the end of its segment (the last dim of a segment hops into the next one)
-          long long end_l = which == 0 ? (long long)seg_first[s] - tile0 : (long long)li + hop_s[li];
-          if (end_l > seg_end_l) end_l = seg_end_l;
-          float acc = 0.0f;
-          for (int k = li; k < (int)end_l; ++k) acc = __fadd_rn(acc, kl_s[k]);
-          const int Kg = candidates_from_kl(acc);
-          starts[g] = tile0 + li;
-          total_kl[g] = acc;
-          K[g] = Kg;
-          group_seed[g] = seed0 + (uint32_t)(g - goff);
-          keys[g] = KEY_INIT;
-          unit_off[g] = my_units;           // relative to this thread's first group; completed below
-          work_off[g] = my_work;
-          my_units += units_of(Kg);
-          my_work += work_of(Kg, (int)end_l - li);
-          if (g_first < 0) g_first = g;
-          ++g_count;
-        }
-      }
+      if (is_seg) slot_s[nodes + sstarts] = (uint16_t)li;
+      if (is_node) slot_s[nodes + sstarts + is_seg] = (uint16_t)(li | 0x8000);
       nodes += is_node;
       sstarts += is_seg;
       gid[tile0 + li] = (int)(B + nodes + sstarts) - 1;
     }
   }
-  ull tot_u, tot_w;
-  ull upre = block_exclusive_scan<ull>(my_units, sm_scan, tot_u);
-  ull wpre = block_exclusive_scan<ull>(my_work, sm_scan, tot_w);
-  // prefixes relative to the tile; the tile's totals are published for k_front_prefix, which completes them
-  for (int k = 0; k < g_count; ++k) {
-    unit_off[g_first + k] += upre;
-    work_off[g_first + k] += wpre;
+  __syncthreads();
+  // Pass 2, one thread per GROUP (the sequential fp32 total, the candidate count and five stores are ~10x the work of a
+  // dim, and only one dim in ~8-12 starts a group: done per dim it ran with most lanes idle): rounds of FRONT_THREADS slots,
+  // the running unit / work prefix carried from round to round.
+  const int n_slots = (int)(node_pre[W - 1] + __popc(node_w[W - 1]) + seg_pre[W - 1] + __popc(seg_w[W - 1]));
+  ull tot_u = 0, tot_w = 0;
+  for (int base_slot = 0; base_slot < n_slots; base_slot += FRONT_THREADS) {
+    const int slot = base_slot + tid;
+    ull my_units = 0, my_work = 0;
+    long long g = -1;
+    if (slot < n_slots) {
+      const uint32_t e = slot_s[slot];
+      const int li = (int)(e & 0x7fffu);
+      const bool forced = (e & 0x8000u) == 0u;          // the segment's forced first group; else a chain node's group
+      const int s = one_seg ? slo : find_segment_between(segs, slo, shi, tile0 + li);
+      const cwq_segment& sg = segs[s];
+      const long long seg_end_l = sg.end - tile0;
+      g = (long long)B + slot;
+      // a node's group ends at the next node -- or at the end of its segment (the last dim of a segment hops into the next one)
+      long long end_l = forced ? (long long)seg_first[s] - tile0 : (long long)li + hop_s[li];
+      if (end_l > seg_end_l) end_l = seg_end_l;
+      float acc = 0.0f;
+      for (int k = li; k < (int)end_l; ++k) acc = __fadd_rn(acc, kl_s[k]);
+      const int Kg = candidates_from_kl(acc);
+      starts[g] = tile0 + li;
+      total_kl[g] = acc;
+      K[g] = Kg;
+      group_seed[g] = sg.seed + (uint32_t)(g - seg_group_off[s]);
+      keys[g] = KEY_INIT;
+      my_units = units_of(Kg);
+      my_work = work_of(Kg, (int)end_l - li);
+    }
+    ull ru, rw;
+    const ull upre = block_exclusive_scan<ull>(my_units, sm_scan, ru);
+    const ull wpre = block_exclusive_scan<ull>(my_work, sm_scan, rw);
+    // prefixes relative to the tile; the tile's totals are published for k_front_prefix, which completes them
+    if (g >= 0) {
+      unit_off[g] = tot_u + upre;
+      work_off[g] = tot_w + wpre;
+    }
+    tot_u += ru;
+    tot_w += rw;
   }
   if (tid == 0) {
     const TilePrefix<2> tp = TilePrefix<2>::carve(prefix_words, n_tiles);
@@ -668,7 +678,7 @@ bool front_plan(long long n, long long max_group_size, FrontPlan* p) {
     const size_t smem_tiles = (size_t)(T + E) * 4 + (size_t)E * (T / 32) * 4 + (size_t)T + 64;
     if (smem_chain <= 200 * 1024 && smem_tiles <= 160 * 1024) {
       p->T = T; p->E = E; p->W = T / 32; p->n_tiles = nt;
-      p->smem_tiles = smem_tiles; p->smem_chain = smem_chain; p->smem_groups = (size_t)(T + E) * 4 + (size_t)4 * (T / 32) * 4 + (size_t)T;
+      p->smem_tiles = smem_tiles; p->smem_chain = smem_chain; p->smem_groups = (size_t)(T + E) * 4 + (size_t)4 * (T / 32) * 4 + (size_t)T + (size_t)4 * T;
       return true;
     }
   }

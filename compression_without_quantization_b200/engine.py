@@ -296,7 +296,10 @@ def _forced_groups(starts_host_per_segment, table, device):
     flat = []
     seg_off = [0]
     for s, st in enumerate(starts_host_per_segment):
-        st = np.asarray(st, dtype=np.int64).reshape(-1)
+        if isinstance(st, list):
+            st = np.fromiter(st, dtype=np.int64, count=len(st))     # the reference hands Python lists over (pln.py:735-741)
+        else:
+            st = np.asarray(st, dtype=np.int64).reshape(-1)
         if st.size < 2 or st[0] != 0 or st[-1] != table.specs[s].n or np.any(np.diff(st) < 0):
             raise CwqError("group_start_indices must start at 0, end at the number of dimensions and be sorted")
         flat.append(st[:-1] + table.starts[s])
