@@ -223,11 +223,15 @@ SLICE_MIN_DIMS = 1 << 20
 
 
 def _chunk_weights(world):
-    """Relative sizes of the chunks of a pipelined batch.  One GPU: 1:3:3:1 -- the upload of the first chunk and the
-    download + formatting of the last are the only stages nothing overlaps, so both are small.  Sharded runs move 1/world
-    of the bytes per rank while every extra chunk still costs its fixed stages, so fewer chunks win (measured on 2 and
-    8 GPUs, tools/profile_pipeline.py): 1:6:1 on 2-3 ranks, 1:3 from 4 ranks on."""
+    """Relative sizes of the chunks of a pipelined batch.  One GPU: 1:11:11:1 -- the upload of the first chunk and the
+    download + formatting of the last are the only stages nothing overlaps, so both are as small as whole calls allow
+    (one image of the 24-image batch; measured with tools/profile_pipeline.py: 108.37 ms end to end against 108.51 for
+    1:7:7:1, 108.91 for 1:3:3:1 and 109.41 for two chunks, device time 107.5).  Sharded runs move 1/world of the bytes per
+    rank while every extra chunk still costs its fixed stages, so fewer chunks win (measured on 2 and 8 GPUs): 1:6:1 on
+    2-3 ranks, 1:3 from 4 ranks on."""
     if world <= 1:
+        if PIPELINE_CHUNKS == 4:
+            return [1.0, 11.0, 11.0, 1.0]
         return [1.0] + [3.0] * (PIPELINE_CHUNKS - 2) + [1.0] if PIPELINE_CHUNKS > 2 else [1.0] * max(PIPELINE_CHUNKS, 1)
     if PIPELINE_CHUNKS != 4:                       # an explicit setting (tests, tools) applies to every world size
         return [1.0] + [3.0] * (PIPELINE_CHUNKS - 2) + [1.0] if PIPELINE_CHUNKS > 2 else [1.0] * max(PIPELINE_CHUNKS, 1)

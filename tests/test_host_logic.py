@@ -27,6 +27,15 @@ def test_plan_chunks_bench_batch_has_small_first_and_last_chunk():
     assert abs(dims[0] / sum(dims) - 1 / 8) < 0.05 and abs(dims[1] / sum(dims) - 3 / 8) < 0.05
 
 
+def test_single_gpu_chunk_layout_of_the_bench_batch():
+    """The default single-GPU layout keeps the two stages nothing overlaps (first upload, last download + formatting) at
+    one image each; an explicit chunk count keeps the 1:3:...:3:1 rule."""
+    sizes = [2304, 196608] * 24
+    chunks = CIS._plan_chunks(sizes, CIS.PIPELINE_CHUNKS, CIS._chunk_weights(1))
+    assert chunks == [(0, 2), (2, 24), (24, 46), (46, 48)]
+    assert CIS._chunk_weights(2) == [1.0, 6.0, 1.0] and CIS._chunk_weights(8) == [1.0, 3.0]
+
+
 def test_row_blocks_three_per_sixteen_dims():
     sizes = torch.arange(0, 200)
     got = D.row_blocks(sizes).tolist()
