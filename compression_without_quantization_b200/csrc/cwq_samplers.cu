@@ -204,7 +204,8 @@ __device__ __forceinline__ void is_score_range_generic(const float2* __restrict_
 constexpr double LOW_K_MAX_NATS = 12.0 * 0.6931471805599453 - 1.0;   // budgets up to 12 bits per group (CIS:181)
 
 // SMALL: every group has <= 16 dims (the reference defaults): only the register-resident path is compiled in,
-// which keeps the kernel at 64 registers / 4 resident CTAs per SM (measured best).
+// which keeps the kernel at 80 registers without spills / 3 resident CTAs per SM (measured best: 2 CTAs at 112 registers
+// and 4 CTAs at 64 registers with spills are 4 % and 0.5 % slower, profiles/r02_s2_ab_inline_occupancy.log).
 // LOWK: the launch for small KL budgets (<= 12 bits per group: tens to hundreds of candidates, one unit per group).  The
 // per-group bookkeeping weighs as much as the scoring there, so this instantiation drops what it can: when every group is
 // exactly one unit (checked on the device: #units == #groups) the group of a unit needs no search and no unit prefix, and
