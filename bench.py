@@ -287,13 +287,15 @@ def secondary_measurements(dev, n1, n2):
             job = E.ISJob(t[0], t[1], t[2], t[3], specs).launch(7)
         torch.cuda.synchronize()
         lib.cwq_profile_enable(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            job = E.ISJob(t[0], t[1], t[2], t[3], specs).launch(7)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        ms = float("inf")
+        for _ in range(2):      # best of two runs of `steps` back-to-back steps: a one-off cudaMalloc of the caching allocator
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # otherwise lands in a 0.2 ms step
+            e0.record()
+            for _ in range(steps):
+                job = E.ISJob(t[0], t[1], t[2], t[3], specs).launch(7)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1) / steps)
         score = []
         for i in range(lib.cwq_profile_count()):
             v = ctypes.c_float(0)
