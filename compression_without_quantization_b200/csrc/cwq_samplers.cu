@@ -3,8 +3,8 @@
 // debug view of the candidate stream.  Reference lines are cited at each extern "C" entry in cwq.h.
 //
 // Work decomposition of the importance sampler (the dominant kernel, k_is_score):
-//   a group's K candidates are cut into UNITs of 1024; a WARP claims a short run of consecutive
-//   units from a global counter, scores 32 candidates at a time (one candidate per lane, its
+//   a group's K candidates are cut into UNITs of 1024; a WARP claims a run of consecutive
+//   units from a global counter (guided: long runs first, single units at the end), scores 32 candidates at a time (one candidate per lane, its
 //   Philox blocks (3 per 16 dims) and Box-Muller pairs generated in registers, never stored), keeps a
 //   per-lane (score, index) best, shuffle-reduces it and publishes one 64-bit atomicMax per run.
 //   No __syncthreads, no HBM traffic beyond the 8 B/dim coefficients and 8 B/group keys.
@@ -33,7 +33,14 @@ constexpr int UNIT_CAND = 1024;  // candidates per unit
 #define CWQ_IS_MIN_BLOCKS 3
 #endif
 
-constexpr int UNIT_BATCH = CWQ_UNIT_BATCH;    // units claimed per atomic
+constexpr int UNIT_BATCH = CWQ_UNIT_BATCH;    // units claimed per atomic (low-K instantiation; the default one is guided)
+#ifndef CWQ_GUIDED_MAX
+#define CWQ_GUIDED_MAX 64
+#endif
+#ifndef CWQ_GUIDED_DIV
+#define CWQ_GUIDED_DIV 4
+#endif
+constexpr int GUIDED_MAX = CWQ_GUIDED_MAX, GUIDED_DIV = CWQ_GUIDED_DIV;
 
 // The scored range of groups is [g0, g1).  Either end may live on the device (g0_dev / g1_dev non-null): g1_dev is the
 // group count of a synchronisation-free encode, (g0_dev, g1_dev) the range a rank computed for itself on the device;
@@ -230,12 +237,31 @@ __global__ void __launch_bounds__(IS_THREADS, CWQ_IS_MIN_BLOCKS) k_is_score(cons
   const ull n_units = unit_off[ng];
   float2* my_coef = reinterpret_cast<float2*>(s_coef[warp]);
   const bool one_each = LOWK && (n_units - u_first) == (ull)ng;      // every group of the range is exactly one unit
+  // Guided self-scheduling (default instantiation): a claim takes 1/GUIDED_DIV of a warp's fair share of the units still
+  // unclaimed, at most GUIDED_MAX and at least one -- long claims while plenty is left (claim, search and staging paid
+  // once per run), single units at the end (the tail of the kernel is one unit long instead of four).  The share comes
+  // from a relaxed read of the counter: a heuristic only, the atomicAdd decides.  Measured against fixed claims of 4 units
+  // (tools/ab_variants.py, same candidate-loop code): 24 images 107.15 -> 106.05 ms, one image 4.644 -> 4.579 ms;
+  // dividing by 2 or 1 instead of 4 loses on one image (units differ in cost), 8 gains less.
+  const ull span_units = n_units - u_first;
+  const ull per_round = (ull)gridDim.x * IS_WARPS * GUIDED_DIV;
   for (;;) {
     ull u = 0;
-    if (lane == 0) u = atomicAdd(counter, (ull)UNIT_BATCH);
+    ull batch = (ull)UNIT_BATCH;
+    if (!LOWK) {
+      if (lane == 0) {
+        const ull seen = ld_volatile_u64(counter);
+        const ull left = seen < span_units ? span_units - seen : 0ull;
+        ull b = left / per_round;
+        b = b < 1ull ? 1ull : (b > (ull)GUIDED_MAX ? (ull)GUIDED_MAX : b);
+        batch = b;
+        u = atomicAdd(counter, b);
+      }
+      batch = __shfl_sync(0xffffffffu, batch, 0);
+    } else if (lane == 0) u = atomicAdd(counter, (ull)UNIT_BATCH);
     u = __shfl_sync(0xffffffffu, u, 0) + u_first;
     if (u >= n_units) break;
-    const ull u_end = u + UNIT_BATCH < n_units ? u + UNIT_BATCH : n_units;
+    const ull u_end = u + batch < n_units ? u + batch : n_units;
     // group of unit u: the largest j with unit_off[j] <= u (unit_off is strictly increasing: every group has a unit).
     // 32-ary search, one probe per lane and round: ~4 rounds of one L2 access instead of 18 dependent ones.
     long long lo = 0, hi = ng - 1;
