@@ -323,17 +323,17 @@ __global__ void __launch_bounds__(IS_THREADS, CWQ_IS_MIN_BLOCKS) k_is_score(cons
       } else if (!SMALL) {
         is_score_range_generic(coef + s, G, sseed, kb, ke, lane, best, bestk);
       }
-      // warp argmax as two REDUX: the largest orderable score, then the lowest index among the lanes that hold it -- the
-      // maximum of pack_key() over the lanes (0 = a lane without a candidate; orderable() of a real score is never 0)
+      // warp argmax; low-K: as two REDUX -- the largest orderable score, then the lowest index among the lanes that hold it,
+      // i.e. the maximum of pack_key() over the lanes (0 = a lane without a candidate; orderable() of a real score is never 0)
       if (LOWK) {
-      const uint32_t sb = bestk == 0xffffffffu ? 0u : orderable(best);
-      const uint32_t top = __reduce_max_sync(0xffffffffu, sb);
-      const uint32_t kmin = __reduce_min_sync(0xffffffffu, sb == top ? bestk : 0xffffffffu);
-      if (lane == 0 && top != 0u) atomicMax(&keys[g], ((ull)top << 32) | (ull)(~kmin));
+        const uint32_t sb = bestk == 0xffffffffu ? 0u : orderable(best);
+        const uint32_t top = __reduce_max_sync(0xffffffffu, sb);
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, sb == top ? bestk : 0xffffffffu);
+        if (lane == 0 && top != 0u) atomicMax(&keys[g], ((ull)top << 32) | (ull)(~kmin));
       } else {
-      ull key = bestk == 0xffffffffu ? 0ull : pack_key(best, bestk);
-      key = warp_max_key(key);
-      if (lane == 0 && key != 0ull) atomicMax(&keys[g], key);
+        ull key = bestk == 0xffffffffu ? 0ull : pack_key(best, bestk);
+        key = warp_max_key(key);
+        if (lane == 0 && key != 0ull) atomicMax(&keys[g], key);
       }
       u = ue;
       ++j;
