@@ -612,6 +612,10 @@ def main():
         # ideal-independent-chains microbenchmark of this kernel's instruction mix: 23.6 cycles per warp-candidate-dim
         # per sub-partition (tools/microbench/overlap.cu "v2 mix", profiles/r01_pipe_overlap_v2_mix.log)
         "frac_of_measured_mix_ceiling": cd_per_s_kernel / (sms * 4 * 32 / 23.6 * f_max),
+        "mix_ceiling_note": "denominator = what tools/microbench/overlap reached issuing the ROUND-1 instruction mix of this loop as "
+                            "ideal independent chains (23.6 cycles per warp-candidate-dim per sub-partition, 1.58e12 cd/s); the "
+                            "loop has shed instructions since (folded scale factor, skipped half-quads), so ~1.0 means 'as fast as "
+                            "that older, heavier mix could ever run', not 'nothing left'",
         "candidate_dims_per_sec_kernel": cd_per_s_kernel, "kernel_ms": score_ms_max,
         "kernel_share_of_step": score_ms_max / ms_per_step if ms_per_step > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture, per launch; null when the capture is not of this
