@@ -70,6 +70,21 @@ def test_candidate_loop_instruction_mix(sass):
     assert not any(x.split()[0].split(".")[0] in ("LDL", "STL", "SHFL", "BAR", "LDG", "STG", "ATOM", "ATOMG", "RED") for x in full[0])
 
 
+def test_greedy_candidate_loop_instruction_mix(sass):
+    """One 16-dim unit of one candidate in both greedy kernels: the same Philox / Box-Muller work as the
+    importance sampler's loop plus 11 shared-memory loads (8 of (c, e) pairs, 3 of block constants) and 2 FFMA per dim."""
+    funcs, _ = sass
+    for kernel in ("k_greedy_encode", "k_greedy_lockstep"):
+        ins = _find(funcs, kernel)
+        unit = [b for b in _loops(ins) if sum("MUFU" in x for x in b) == 32 and len(b) < 300]
+        assert len(unit) == 1, kernel
+        ops = collections.Counter(x.split()[0].split(".")[0] for x in unit[0])
+        assert ops["MUFU"] == 32 and ops["LDS"] == 11 and ops["LOP3"] + ops["PRMT"] == 72, (kernel, ops)
+        assert 44 <= ops["IMAD"] <= 46 and ops["FFMA"] + ops["FMUL"] + ops["FADD"] == 72, (kernel, ops)
+        assert len(unit[0]) <= 240, (kernel, len(unit[0]))
+        assert not any(x.startswith(("LDL", "STL")) for x in unit[0]), kernel
+
+
 def test_no_local_memory_in_any_candidate_loop(sass):
     funcs, _ = sass
     for name, ins in funcs.items():
